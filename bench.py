@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — all-pairs GCUPS of the alignment hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one full all-pairs job (getMinimumPenalties) over the named synthetic workload:
+every pair's DP fill + traceback + per-pair SHA-512 on the GPU(s), gather in the reference's
+task order, ordered hash chain on rank 0.  `value` = cells / step time with the sequences
+already resident in HBM and the batches planned; `e2e` = the same job through the public
+call with HOST buffers (H2D of the inputs, D2H of penalties + digests, chain) in the timed
+region.  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "multiple-sequence-alignment-openmp-openmpi_b200"
+OPS_PER_CELL = 10  # algorithmic int32 lane-ops per DP cell
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4")
+    ap.add_argument("--nchunks", type=int, default=0, help="gather/fold chunks (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # "under load" = samples drawing real power
+        load = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(genes, n_seq=16):
+    """Bounded CPU sample of the workload: its first n_seq sequences, all pairs among them."""
+    return genes[:n_seq]
+
+
+def run_cpu_baseline(workloads, pxy, pgap, genes, workload_name):
+    """The reference's own CPU implementation (oracle/_ref/ref_par = unmodified
+    submit/xuliny-seqalkway.cpp + single-rank mpi.h shim) if it was built, else the oracle port."""
+    from oracle import binding as oracle  # checker / baseline only
+
+    n_seq = 2 if len(genes) == 2 else 16
+    sample = cpu_sample(genes, n_seq)
+    if len(genes) == 2:  # cfg5: the reference cannot allocate 200k x 200k ints; 50 000^2 prefix
+        sample = [g[:50000] for g in genes]
+    cells = workloads.total_cells(sample)
+    doc = workloads.format_input(pxy, pgap, sample)
+    ncpu = os.cpu_count() or 1
+    desc = f"{workload_name}: first {len(sample)} sequences, {len(sample) * (len(sample) - 1) // 2} pairs, {cells} cells"
+    if os.path.exists(oracle.REF_PAR):
+        t_us, digest, pen = oracle.run_reference(oracle.REF_PAR, doc)
+        # the submission hard-codes 15 compute + 2 control threads on rank 0 (:94,238,272,425)
+        return {"value": cells / (t_us * 1e-6) / 1e9, "unit": "GCUPS", "cores": min(ncpu, 17), "kind": "reference",
+                "threads": 17, "host_cpus": ncpu, "sample": desc, "seconds": t_us * 1e-6, "digest": digest}
+    t0 = time.perf_counter()
+    digest, pen, _ = oracle.all_pairs(sample, pxy, pgap, nthreads=0)
+    dt = time.perf_counter() - t0
+    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": ncpu, "kind": "port", "host_cpus": ncpu,
+            "sample": desc, "seconds": dt, "digest": digest}
+
+
+def main_reference(args, rank):
+    """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    workloads = importlib.import_module(PKG + ".workloads")
+    pxy, pgap, genes = workloads.make(args.workload)
+    vals, base = [], None
+    for it in range(args.warmup + args.steps):
+        # one warm-up is enough to page the binary in; the rest would only burn minutes
+        if it < args.warmup and it > 0:
+            continue
+        base = run_cpu_baseline(workloads, pxy, pgap, genes, args.workload)
+        if it >= args.warmup:
+            vals.append(base["value"])
+    v = statistics.mean(vals)
+    base["value"] = v
+    line = {"impl": "reference", "metric": "all-pairs GCUPS", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": {"workload": workloads.CONFIGS[args.workload][0], "pxy": pxy, "pgap": pgap,
+                                            "sample": base["sample"]},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return main_reference(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    pkg = importlib.import_module(PKG)
+    workloads = importlib.import_module(PKG + ".workloads")
+    dmod = importlib.import_module(PKG + ".distributed")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: seqalk-b200 has no CPU fallback")
+    pkg.lib()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus and rank == 0:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    pxy, pgap, genes = workloads.make(args.workload)
+    lens = [len(g) for g in genes]
+    cells = workloads.total_cells(genes)
+    T = len(genes) * (len(genes) - 1) // 2
+    nchunks = args.nchunks or (8 if (world > 1 and T >= 4096) else 1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peaks = pkg.measure_int_peaks(local_rank) if rank == 0 else None
+
+    # ---- value: inputs resident in HBM, batches planned
+    plan = dmod.ShardPlan(lens, world, nchunks)
+    shard = dmod.GpuShard(genes, pxy, pgap, plan, rank, local_rank)
+    result = None
+
+    def step_resident():
+        nonlocal result
+        result = dmod.run_sharded(plan, rank, shard.run_chunk)
+
+    for _ in range(args.warmup):
+        barrier()
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    step_s, fill_ms, tb_ms, dg_ms, launches, dir_bytes = [], 0.0, 0.0, 0.0, 0, 0
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        step_resident()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        step_s.append(max_over_ranks(dt))
+        st = shard.stats()
+        fill_ms += sum(s.fill_ms for s in st)
+        tb_ms += sum(s.traceback_ms for s in st)
+        dg_ms += sum(s.digest_ms for s in st)
+        launches += sum(s.fill_launches + s.traceback_launches + s.digest_launches for s in st)
+        dir_bytes = sum(s.dir_bytes for s in st)
+        my_cells = sum(s.cells for s in st)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    digest_resident = result[0] if rank == 0 else None
+    shard.close()
+    del shard
+
+    # per-rank device-side kernel time (CUDA events on the launching streams), max over ranks
+    fill_ms_max = max_over_ranks(fill_ms / args.steps)
+    total_launches = int(sum_over_ranks(float(launches)))
+    # the slowest rank bounds the step: its fill rate is the dominant-kernel figure
+    my_rate = (my_cells * OPS_PER_CELL) / (fill_ms / args.steps * 1e-3) if fill_ms > 0 else 0.0
+    agg_ops_rate = sum_over_ranks(my_rate)
+    agg_dir_rate = sum_over_ranks(dir_bytes / (fill_ms / args.steps * 1e-3) if fill_ms > 0 else 0.0)
+
+    # ---- e2e: host buffers in, host results out, through the public call
+    e2e_s = []
+    h2d = sum(lens) if world == 1 else sum(lens)  # every rank uploads the (replicated) inputs
+    d2h = T * 68
+    digest_e2e = None
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            digest_e2e, pen_e2e = pkg.get_minimum_penalties(genes, pxy, pgap)
+        else:
+            r = dmod.all_pairs_distributed(genes, pxy, pgap, nchunks=nchunks, device=local_rank)
+            if rank == 0:
+                digest_e2e, pen_e2e = r
+        torch.cuda.synchronize()
+        e2e_s.append(max_over_ranks(time.perf_counter() - t0))
+    barrier()
+
+    if rank == 0:
+        ms = statistics.mean(step_s) * 1e3
+        value = cells / (ms * 1e-3) / 1e9
+        e2e_ms = statistics.mean(e2e_s) * 1e3
+        peak = peaks["lop3"]
+        sm_mhz = clocks.get("sm_mhz") or 0
+        line = {
+            "metric": "all-pairs GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workloads.CONFIGS[args.workload][0], "name": args.workload, "pxy": pxy,
+                       "pgap": pgap, "k": len(genes), "pairs": T, "cells": cells, "sharding": f"lpt-cells x{world}",
+                       "gather_chunks": nchunks,
+                       "l2": "working set (packed directions, GBs per batch) far exceeds the 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h},
+            "gpu_launches": total_launches,
+            "roofline": {
+                "bound": "int_alu", "achieved": agg_ops_rate / world / 1e9, "peak": peak / 1e9, "unit": "Gop/s",
+                "frac": (agg_ops_rate / world) / peak if peak else None, "traffic": None,
+                "per": "GPU (mean over ranks)", "ops_per_cell": OPS_PER_CELL,
+                "peak_source": "measured live: dependent-free LOP3 issue rate (seqalk_measure_int_peaks), ALU pipe",
+                "peak_nominal_at_sm_mhz": 148 * 64 * sm_mhz * 1e6 / 1e9 if sm_mhz else None,
+                "issue_rates_gops": {k: v / 1e9 for k, v in peaks.items()},
+                "fill_gcups_per_gpu": agg_ops_rate / world / OPS_PER_CELL / 1e9,
+                "fill_ms_per_step_max_rank": fill_ms_max,
+                "hbm": {"bound": "hbm", "achieved": agg_dir_rate / world / 1e9, "unit": "GB/s",
+                        "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
+                        "note": "algorithmic bytes = 0.25 B/cell of packed directions written by the fill"},
+            },
+            "kernel_ms_per_step": {"fill": fill_ms / args.steps, "traceback": tb_ms / args.steps,
+                                   "digest": dg_ms / args.steps, "note": "rank 0, CUDA events on the launching streams"},
+            "digest": digest_resident, "digest_e2e_matches": digest_resident == digest_e2e,
+        }
+        line["roofline"]["hbm"]["frac"] = line["roofline"]["hbm"]["achieved"] / line["roofline"]["hbm"]["peak"]
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = run_cpu_baseline(workloads, pxy, pgap, genes, args.workload)
+            except Exception as e:  # the baseline must never sink the GPU number
+                line["cpu_baseline"] = {"value": None, "error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

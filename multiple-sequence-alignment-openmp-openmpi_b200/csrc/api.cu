@@ -1,0 +1,406 @@
+// api.cu — the C ABI of include/seqalk.h over the engine (host code only).
+#include "../../include/seqalk.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "engine.h"
+#include "sha512_host.h"
+
+using namespace seqalk;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Runtime {
+  std::mutex mu;
+  std::vector<std::unique_ptr<DeviceWorker>> workers;  // devices 0..n-1
+  bool peer_ok = false;                                 // every worker can store into device 0
+};
+Runtime &rt() {
+  static Runtime r;
+  return r;
+}
+
+int fail(const std::exception &e) {
+  g_last_error = e.what();
+  return 1;
+}
+int fail(const char *msg) {
+  g_last_error = msg;
+  return 1;
+}
+
+void init_locked(Runtime &r, int ngpus) {
+  int visible = 0;
+  cudaError_t e = cudaGetDeviceCount(&visible);
+  if (e != cudaSuccess || visible < 1) {
+    cudaGetLastError();
+    throw std::runtime_error(
+        "no CUDA device visible: libseqalk has no CPU fallback (needs an sm_100a GPU)");
+  }
+  if (ngpus <= 0 || ngpus > visible) ngpus = visible;
+  r.workers.clear();
+  for (int d = 0; d < ngpus; ++d) r.workers.emplace_back(new DeviceWorker(d));
+  // fused gather: let every device store its results straight into device 0's arrays
+  r.peer_ok = ngpus > 1;
+  for (int d = 1; d < ngpus && r.peer_ok; ++d) {
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, d, 0) != cudaSuccess || !can) {
+      r.peer_ok = false;
+      break;
+    }
+    SEQALK_CUDA(cudaSetDevice(d));
+    cudaError_t pe = cudaDeviceEnablePeerAccess(0, 0);
+    if (pe == cudaErrorPeerAccessAlreadyEnabled) {
+      cudaGetLastError();
+    } else if (pe != cudaSuccess) {
+      cudaGetLastError();
+      r.peer_ok = false;
+    }
+  }
+  if (const char *env = std::getenv("SEQALK_P2P"))
+    if (!std::atoi(env)) r.peer_ok = false;
+}
+
+void ensure_init(Runtime &r) {
+  if (!r.workers.empty()) return;
+  int n = 1;
+  if (const char *e = std::getenv("SEQALK_GPUS")) n = std::atoi(e);
+  init_locked(r, n);
+}
+
+struct DeviceArray {
+  int dev;
+  void *p = nullptr;
+  DeviceArray(int d, size_t bytes) : dev(d) {
+    SEQALK_CUDA(cudaSetDevice(dev));
+    SEQALK_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+  }
+  ~DeviceArray() {
+    cudaSetDevice(dev);
+    cudaFree(p);
+  }
+};
+
+// all tasks of `tasks` on the runtime's GPUs; results in task order on the host
+void run_tasks(Runtime &r, const SeqPack &pack, const std::vector<TaskIJ> &tasks, int pxy, int pgap,
+               int32_t *penalties, uint8_t *digests) {
+  const int N = (int)r.workers.size();
+  const size_t T = tasks.size();
+  if (N == 1) {
+    DeviceWorker &w = *r.workers[0];
+    w.load(pack);
+    w.plan(tasks, pxy, pgap);
+    w.run();
+    w.fetch(penalties, digests);
+    return;
+  }
+  // shard by cells (LPT), one host thread per GPU
+  std::vector<std::vector<TaskIJ>> shard(N);
+  std::vector<std::vector<uint32_t>> slots(N);
+  {
+    struct Item {
+      uint64_t cells;
+      uint32_t idx;
+    };
+    std::vector<Item> items(T);
+    for (size_t t = 0; t < T; ++t)
+      items[t] = Item{(uint64_t)pack.len[tasks[t].i] * (uint64_t)pack.len[tasks[t].j], (uint32_t)t};
+    std::sort(items.begin(), items.end(),
+              [](const Item &a, const Item &b) { return a.cells != b.cells ? a.cells > b.cells : a.idx < b.idx; });
+    std::vector<uint64_t> load(N, 0);
+    std::vector<std::vector<uint32_t>> idx(N);
+    for (const Item &it : items) {
+      int best = 0;
+      for (int d = 1; d < N; ++d)
+        if (load[d] < load[best]) best = d;
+      load[best] += it.cells;
+      idx[best].push_back(it.idx);
+    }
+    for (int d = 0; d < N; ++d) {
+      std::sort(idx[d].begin(), idx[d].end());
+      for (uint32_t t : idx[d]) {
+        shard[d].push_back(tasks[t]);
+        slots[d].push_back(t);
+      }
+    }
+  }
+  std::unique_ptr<DeviceArray> pen0, dig0;
+  if (r.peer_ok) {
+    pen0.reset(new DeviceArray(0, T * sizeof(int32_t)));
+    dig0.reset(new DeviceArray(0, T * 64));
+  }
+  std::vector<std::string> errors(N);
+  std::vector<std::vector<int32_t>> lpen(N);
+  std::vector<std::vector<uint8_t>> ldig(N);
+  std::vector<std::thread> threads;
+  for (int d = 0; d < N; ++d) {
+    threads.emplace_back([&, d]() {
+      try {
+        DeviceWorker &w = *r.workers[d];
+        w.load(pack);
+        if (r.peer_ok) {
+          // results land in device 0's task-ordered arrays through peer stores issued by
+          // the digest kernel itself (gather fused into the producing kernel, over NVLink)
+          w.plan(shard[d], pxy, pgap, &slots[d]);
+          w.run(static_cast<int32_t *>(pen0->p), static_cast<uint8_t *>(dig0->p));
+        } else {
+          w.plan(shard[d], pxy, pgap);
+          w.run();
+          lpen[d].resize(shard[d].size());
+          ldig[d].resize(shard[d].size() * 64);
+          w.fetch(lpen[d].data(), ldig[d].data());
+        }
+      } catch (const std::exception &e) {
+        errors[d] = e.what();
+        if (errors[d].empty()) errors[d] = "unknown error";
+      }
+    });
+  }
+  for (std::thread &t : threads) t.join();
+  for (int d = 0; d < N; ++d)
+    if (!errors[d].empty()) throw std::runtime_error("GPU " + std::to_string(d) + ": " + errors[d]);
+  if (r.peer_ok) {
+    SEQALK_CUDA(cudaSetDevice(0));
+    SEQALK_CUDA(cudaMemcpy(penalties, pen0->p, T * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    SEQALK_CUDA(cudaMemcpy(digests, dig0->p, T * 64, cudaMemcpyDeviceToHost));
+  } else {
+    for (int d = 0; d < N; ++d)
+      for (size_t s = 0; s < slots[d].size(); ++s) {
+        penalties[slots[d][s]] = lpen[d][s];
+        std::memcpy(digests + 64ull * slots[d][s], ldig[d].data() + 64 * s, 64);
+      }
+  }
+}
+
+}  // namespace
+
+struct seqalk_job {
+  std::unique_ptr<DeviceWorker> worker;
+};
+
+extern "C" {
+
+int seqalk_init(int ngpus) {
+  try {
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> g(r.mu);
+    init_locked(r, ngpus);
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+void seqalk_shutdown(void) {
+  Runtime &r = rt();
+  std::lock_guard<std::mutex> g(r.mu);
+  r.workers.clear();
+}
+
+int seqalk_device_count(void) {
+  Runtime &r = rt();
+  std::lock_guard<std::mutex> g(r.mu);
+  return (int)r.workers.size();
+}
+
+const char *seqalk_last_error(void) { return g_last_error.c_str(); }
+const char *seqalk_version(void) { return "seqalk-b200 0.1 (sm_100a)"; }
+
+int seqalk_all_pairs(const char *const *seqs, const int32_t *lens, int32_t k, int32_t pxy, int32_t pgap,
+                     int32_t *penalties_out, char digest_hex_out[129]) {
+  try {
+    if (!seqs || !lens || !penalties_out || !digest_hex_out) return fail("null argument");
+    if (k < 2) return fail("k < 2 is undefined in the reference");
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> g(r.mu);
+    ensure_init(r);
+    SeqPack pack;
+    pack.build(seqs, lens, k);
+    std::vector<TaskIJ> tasks;
+    all_tasks(k, tasks);
+    std::vector<uint8_t> digests(tasks.size() * 64);
+    run_tasks(r, pack, tasks, pxy, pgap, penalties_out, digests.data());
+    size_t hl = 0;
+    digest_hex_out[0] = 0;
+    fold_chain(digests.data(), tasks.size(), digest_hex_out, &hl);
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_pair(const char *x, int32_t m, const char *y, int32_t n, int32_t pxy, int32_t pgap, int32_t *xans,
+                int32_t *yans, int32_t *penalty_out) {
+  try {
+    if (!x || !y) return fail("null argument");
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> g(r.mu);
+    ensure_init(r);
+    const char *seqs[2] = {y, x};  // task (i=1, j=0): x = seqs[1] rows, y = seqs[0] columns
+    const int32_t lens[2] = {n, m};
+    SeqPack pack;
+    pack.build(seqs, lens, 2);
+    std::vector<TaskIJ> tasks(1, TaskIJ{1, 0});
+    DeviceWorker &w = *r.workers[0];
+    w.load(pack);
+    w.plan(tasks, pxy, pgap);
+    w.run();
+    int32_t pen = 0;
+    w.fetch(&pen, nullptr);
+    if (penalty_out) *penalty_out = pen;
+    if (xans || yans) {
+      std::vector<uint8_t> a1, a2;
+      if (!w.fetch_alignment(0, a1, a2)) return fail("alignment not available");
+      const size_t l = (size_t)m + (size_t)n, L = a1.size();
+      // right-aligned int arrays, '_' pad in front (submit/xuliny-seqalkway.cpp:535-558)
+      for (size_t a = 1; a <= l; ++a) {
+        const bool pad = a <= l - L;
+        if (xans) xans[a] = pad ? (int32_t)'_' : (int32_t)(char)a1[a - 1 - (l - L)];
+        if (yans) yans[a] = pad ? (int32_t)'_' : (int32_t)(char)a2[a - 1 - (l - L)];
+      }
+    }
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int64_t seqalk_num_tasks(int32_t k) { return k < 2 ? 0 : (int64_t)k * (k - 1) / 2; }
+
+int seqalk_task_ij(int64_t task_id, int32_t *i_out, int32_t *j_out) {
+  if (task_id < 0 || !i_out || !j_out) return fail("bad argument");
+  task_from_id(task_id, i_out, j_out);
+  return 0;
+}
+
+int seqalk_partition(const int32_t *lens, int32_t k, int64_t id_begin, int64_t id_end, int32_t nranks,
+                     int32_t rank, int64_t *ids_out, int64_t *count_out) {
+  try {
+    if (!lens || !ids_out || !count_out || nranks < 1 || rank < 0 || rank >= nranks) return fail("bad argument");
+    if (id_begin < 0 || id_end > seqalk_num_tasks(k) || id_begin > id_end) return fail("task id range out of bounds");
+    std::vector<std::vector<int64_t>> per;
+    partition_lpt(lens, k, id_begin, id_end, nranks, per);
+    *count_out = (int64_t)per[rank].size();
+    std::copy(per[rank].begin(), per[rank].end(), ids_out);
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_partition_all(const int32_t *lens, int32_t k, int64_t id_begin, int64_t id_end, int32_t nranks,
+                         int64_t *ids_out, int64_t *counts_out) {
+  try {
+    if (!lens || !ids_out || !counts_out || nranks < 1) return fail("bad argument");
+    if (id_begin < 0 || id_end > seqalk_num_tasks(k) || id_begin > id_end) return fail("task id range out of bounds");
+    std::vector<std::vector<int64_t>> per;
+    partition_lpt(lens, k, id_begin, id_end, nranks, per);
+    int64_t *w = ids_out;
+    for (int r = 0; r < nranks; ++r) {
+      counts_out[r] = (int64_t)per[r].size();
+      w = std::copy(per[r].begin(), per[r].end(), w);
+    }
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_create(int32_t device, const char *const *seqs, const int32_t *lens, int32_t k, int32_t pxy,
+                      int32_t pgap, const int64_t *task_ids, int64_t ntasks, seqalk_job_t **job_out) {
+  try {
+    if (!seqs || !lens || !job_out || k < 2) return fail("bad argument");
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1) {
+      cudaGetLastError();
+      return fail("no CUDA device visible: libseqalk has no CPU fallback (needs an sm_100a GPU)");
+    }
+    if (device < 0 || device >= visible) return fail("device index out of range");
+    SeqPack pack;
+    pack.build(seqs, lens, k);
+    std::vector<TaskIJ> tasks;
+    if (task_ids) {
+      const int64_t T = seqalk_num_tasks(k);
+      tasks.resize((size_t)ntasks);
+      for (int64_t t = 0; t < ntasks; ++t) {
+        if (task_ids[t] < 0 || task_ids[t] >= T) return fail("task id out of range");
+        task_from_id(task_ids[t], &tasks[t].i, &tasks[t].j);
+      }
+    } else {
+      all_tasks(k, tasks);
+    }
+    std::unique_ptr<seqalk_job> job(new seqalk_job);
+    job->worker.reset(new DeviceWorker(device));
+    job->worker->load(pack);
+    job->worker->plan(tasks, pxy, pgap);
+    *job_out = job.release();
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_run(seqalk_job_t *job, void *penalties_dev, void *digests_dev) {
+  try {
+    if (!job) return fail("null job");
+    job->worker->run(static_cast<int32_t *>(penalties_dev), static_cast<uint8_t *>(digests_dev));
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_fetch(seqalk_job_t *job, int32_t *penalties_out, uint8_t *digests_out) {
+  try {
+    if (!job) return fail("null job");
+    job->worker->fetch(penalties_out, digests_out);
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_stats(const seqalk_job_t *job, seqalk_stats_t *s) {
+  if (!job || !s) return fail("null argument");
+  const JobStats &j = job->worker->stats();
+  s->cells = j.cells;
+  s->dir_bytes = j.dir_bytes;
+  s->batches = j.batches;
+  s->fill_launches = j.fill_launches;
+  s->traceback_launches = j.traceback_launches;
+  s->digest_launches = j.digest_launches;
+  s->fill_ms = j.fill_ms;
+  s->traceback_ms = j.traceback_ms;
+  s->digest_ms = j.digest_ms;
+  s->wall_ms = j.wall_ms;
+  return 0;
+}
+
+void seqalk_job_destroy(seqalk_job_t *job) { delete job; }
+
+int seqalk_fold_chain(const uint8_t *pair_digests, int64_t count, char state_hex[129]) {
+  if (!state_hex || count < 0 || (count && !pair_digests)) return fail("bad argument");
+  size_t hl = std::strlen(state_hex);
+  if (hl != 0 && hl != 128) return fail("chain state must be \"\" or 128 hex chars");
+  fold_chain(pair_digests, (size_t)count, state_hex, &hl);
+  return 0;
+}
+
+int seqalk_sha512_hex(const void *data, size_t len, char out[129]) {
+  if (!out || (len && !data)) return fail("bad argument");
+  Sha512::hex(data, len, out);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+// engine.cu — see engine.h
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <queue>
+#include <stdexcept>
+
+namespace seqalk {
+
+void throw_cuda(cudaError_t e, const char *what, const char *file, int line) {
+  if (e == cudaSuccess) return;
+  char buf[512];
+  std::snprintf(buf, sizeof buf, "CUDA error %s (%d) at %s:%d: %s", cudaGetErrorString(e), (int)e, file, line,
+                what);
+  throw std::runtime_error(buf);
+}
+
+static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
+  k = k_;
+  off.resize(k);
+  len.assign(lens, lens + k);
+  size_t total = 0;
+  for (int i = 0; i < k; ++i) {
+    if (lens[i] < 0) throw std::runtime_error("negative sequence length");
+    off[i] = (uint32_t)total;
+    total += round_up((size_t)lens[i], 16) + 16;
+    if (total > 0xfff00000ull) throw std::runtime_error("input larger than 4 GiB is not supported");
+  }
+  bytes.assign(total + BUFFER_SLACK, 0);
+  for (int i = 0; i < k; ++i) std::memcpy(bytes.data() + off[i], seqs[i], (size_t)lens[i]);
+}
+
+uint64_t total_cells(const SeqPack &pack, const std::vector<TaskIJ> &tasks) {
+  uint64_t c = 0;
+  for (const TaskIJ &t : tasks) c += (uint64_t)pack.len[t.i] * (uint64_t)pack.len[t.j];
+  return c;
+}
+
+void all_tasks(int k, std::vector<TaskIJ> &out) {
+  out.clear();
+  out.reserve((size_t)k * (k - 1) / 2);
+  for (int i = 1; i < k; ++i)
+    for (int j = 0; j < i; ++j) out.push_back(TaskIJ{i, j});
+}
+
+void task_from_id(int64_t id, int32_t *i, int32_t *j) {
+  // largest i with i(i-1)/2 <= id
+  int64_t ii = (int64_t)((1.0 + std::sqrt(1.0 + 8.0 * (double)id)) / 2.0);
+  while (ii * (ii - 1) / 2 > id) --ii;
+  while ((ii + 1) * ii / 2 <= id) ++ii;
+  *i = (int32_t)ii;
+  *j = (int32_t)(id - ii * (ii - 1) / 2);
+}
+
+void partition_lpt(const int32_t *lens, int k, int64_t id_begin, int64_t id_end, int nranks,
+                   std::vector<std::vector<int64_t>> &per_rank) {
+  (void)k;
+  per_rank.assign(nranks, {});
+  if (id_end <= id_begin) return;
+  struct Item {
+    uint64_t cells;
+    int64_t id;
+  };
+  std::vector<Item> items;
+  items.reserve((size_t)(id_end - id_begin));
+  int32_t i, j;
+  task_from_id(id_begin, &i, &j);
+  for (int64_t id = id_begin; id < id_end; ++id) {
+    items.push_back(Item{(uint64_t)lens[i] * (uint64_t)lens[j], id});
+    if (++j == i) {
+      ++i;
+      j = 0;
+    }
+  }
+  std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+    return a.cells != b.cells ? a.cells > b.cells : a.id < b.id;
+  });
+  // min-heap of (load, rank)
+  typedef std::pair<uint64_t, int> LR;
+  std::priority_queue<LR, std::vector<LR>, std::greater<LR>> heap;
+  for (int r = 0; r < nranks; ++r) heap.push(LR(0, r));
+  for (const Item &it : items) {
+    LR top = heap.top();
+    heap.pop();
+    per_rank[top.second].push_back(it.id);
+    top.first += it.cells;
+    heap.push(top);
+  }
+  for (int r = 0; r < nranks; ++r) std::sort(per_rank[r].begin(), per_rank[r].end());
+}
+
+// ------------------------------------------------------------------ DeviceWorker
+
+DeviceWorker::DeviceWorker(int device) : dev_(device) {
+  SEQALK_CUDA(cudaSetDevice(dev_));
+  cudaDeviceProp prop;
+  SEQALK_CUDA(cudaGetDeviceProperties(&prop, dev_));
+  if (prop.major < 10)
+    throw std::runtime_error(std::string("seqalk needs an sm_100a GPU (B200); found ") + prop.name);
+  sm_count_ = prop.multiProcessorCount;
+  if (const char *e = std::getenv("SEQALK_SLOTS")) nslots_ = std::max(1, std::min(4, std::atoi(e)));
+  size_t free_b = 0, total_b = 0;
+  SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  double budget_gb = 32.0;
+  if (const char *e = std::getenv("SEQALK_DIR_BUDGET_GB")) budget_gb = std::atof(e);
+  dir_budget_ = (size_t)(budget_gb * (double)(1ull << 30));
+  const size_t cap = (size_t)((double)free_b * 0.80 / nslots_);
+  if (dir_budget_ > cap) dir_budget_ = cap;
+  slots_.resize(nslots_);
+  for (Slot &s : slots_) {
+    SEQALK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    SEQALK_CUDA(cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
+  }
+  ensure(err_, sizeof(uint32_t));
+}
+
+void DeviceWorker::release(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+DeviceWorker::~DeviceWorker() {
+  cudaSetDevice(dev_);
+  cudaDeviceSynchronize();
+  for (Slot &s : slots_) {
+    for (DevBuf *b : {&s.pairs, &s.tasks, &s.slots, &s.progress, &s.brow, &s.dirs, &s.out, &s.align, &s.pen,
+                      &s.cost, &s.counter})
+      release(*b);
+    if (s.h_stage) cudaFreeHost(s.h_stage);
+    if (s.staged) cudaEventDestroy(s.staged);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  release(seq_);
+  release(res_pen_);
+  release(res_dig_);
+  release(err_);
+  for (cudaEvent_t e : ev_) cudaEventDestroy(e);
+}
+
+void DeviceWorker::ensure(DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return;
+  // growing a buffer: nothing may still be using the old one
+  SEQALK_CUDA(cudaDeviceSynchronize());
+  release(b);
+  size_t want = round_up(bytes + bytes / 16, 256);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = round_up(bytes, 256);
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
+    char msg[256];
+    std::snprintf(msg, sizeof msg, "getMinimumPenalty: device allocation of %zu bytes failed (%s)", want,
+                  cudaGetErrorString(e));
+    throw std::runtime_error(msg);
+  }
+  b.cap = want;
+}
+
+void DeviceWorker::ensure_stage(Slot &s, size_t bytes) {
+  if (bytes <= s.h_cap) return;
+  if (s.staged_pending) {
+    SEQALK_CUDA(cudaEventSynchronize(s.staged));
+    s.staged_pending = false;
+  }
+  if (s.h_stage) SEQALK_CUDA(cudaFreeHost(s.h_stage));
+  s.h_stage = nullptr;
+  const size_t want = round_up(bytes + bytes / 8, 4096);
+  SEQALK_CUDA(cudaMallocHost(&s.h_stage, want));
+  s.h_cap = want;
+}
+
+void DeviceWorker::load(const SeqPack &pack) {
+  SEQALK_CUDA(cudaSetDevice(dev_));
+  pack_copy_ = pack;  // lengths/offsets are needed for planning; bytes are small (<= MBs)
+  pack_ = &pack_copy_;
+  ensure(seq_, pack.bytes.size());
+  SEQALK_CUDA(cudaMemcpyAsync(seq_.p, pack.bytes.data(), pack.bytes.size(), cudaMemcpyHostToDevice,
+                              slots_[0].stream));
+  SEQALK_CUDA(cudaStreamSynchronize(slots_[0].stream));
+}
+
+void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
+                        const std::vector<uint32_t> *result_slots) {
+  if (!pack_) throw std::runtime_error("plan() before load()");
+  tasks_ = tasks;
+  if (result_slots) {
+    if (result_slots->size() != tasks.size()) throw std::runtime_error("result_slots size mismatch");
+    result_slots_ = *result_slots;
+  } else {
+    result_slots_.clear();
+  }
+  pxy_ = pxy;
+  pgap_ = pgap;
+  batches_.clear();
+  stats_ = JobStats();
+  constexpr int R = FILL_R;
+  int64_t maxlen = 1;
+  Batch cur{0, 0, 0, 0, 0, 0};
+  for (size_t t = 0; t < tasks_.size(); ++t) {
+    const TaskIJ &tk = tasks_[t];
+    if (tk.i < 0 || tk.i >= pack_->k || tk.j < 0 || tk.j >= pack_->k) throw std::runtime_error("task index out of range");
+    const int m = pack_->len[tk.i], n = pack_->len[tk.j];
+    if (m < 1 || n < 1)
+      throw std::runtime_error("empty sequence: undefined in the reference (ceil(0/0) tile size, submit/xuliny-seqalkway.cpp:457)");
+    maxlen = std::max<int64_t>(maxlen, std::max(m, n));
+    const uint32_t ns = (uint32_t)num_strips(m, R);
+    const uint64_t db = (uint64_t)ns * strip_dir_bytes(n, R);
+    if (cur.count && (cur.dir_bytes + db > dir_budget_ || (uint64_t)cur.nstrips + ns > 0x7fffffffull)) {
+      batches_.push_back(cur);
+      cur = Batch{t, 0, 0, 0, 0, 0};
+    }
+    cur.count++;
+    cur.dir_bytes += db;
+    cur.brow_ints += 4ull * (uint64_t)macro_cols(n) + 4;
+    cur.out_bytes += 2ull * round_up((size_t)m + n, 16);
+    cur.nstrips += ns;
+    stats_.cells += (uint64_t)m * (uint64_t)n;
+    stats_.dir_bytes += db;
+  }
+  if (cur.count) batches_.push_back(cur);
+  stats_.batches = (uint32_t)batches_.size();
+  // fast path needs non-negative penalties and scores far from int32 overflow
+  // (|H'| <= 2*max(pxy,pgap)*(m+n)); anything else takes the exact-select kernel.
+  const int64_t pmax = std::max<int64_t>(std::max(pxy, pgap), 1);
+  general_ = pxy < 0 || pgap < 0 || pmax * 4 * maxlen >= (1ll << 29);
+  if (const char *e = std::getenv("SEQALK_FORCE_GENERAL"))
+    if (std::atoi(e)) general_ = true;
+}
+
+void DeviceWorker::run(int32_t *penalties_dev, uint8_t *digests_dev) {
+  SEQALK_CUDA(cudaSetDevice(dev_));
+  const auto t_begin = std::chrono::steady_clock::now();
+  constexpr int R = FILL_R;
+  const size_t T = tasks_.size();
+  if (!penalties_dev) {
+    ensure(res_pen_, std::max<size_t>(T, 1) * sizeof(int32_t));
+    penalties_dev = static_cast<int32_t *>(res_pen_.p);
+  }
+  if (!digests_dev) {
+    ensure(res_dig_, std::max<size_t>(T, 1) * 64);
+    digests_dev = static_cast<uint8_t *>(res_dig_.p);
+  }
+  // events: 4 per batch (fill start/end, traceback end, digest end)
+  while (ev_.size() < 4 * batches_.size()) {
+    cudaEvent_t e;
+    SEQALK_CUDA(cudaEventCreate(&e));
+    ev_.push_back(e);
+  }
+  SEQALK_CUDA(cudaMemsetAsync(err_.p, 0, sizeof(uint32_t), slots_[0].stream));
+  SEQALK_CUDA(cudaStreamSynchronize(slots_[0].stream));
+
+  for (size_t b = 0; b < batches_.size(); ++b) {
+    const Batch &B = batches_[b];
+    Slot &S = slots_[b % nslots_];
+    // ---- size device buffers
+    ensure(S.pairs, B.count * sizeof(PairDesc));
+    ensure(S.tasks, (size_t)B.nstrips * sizeof(StripTask));
+    ensure(S.slots, B.count * sizeof(uint32_t));
+    ensure(S.progress, (size_t)B.nstrips * sizeof(uint32_t));
+    ensure(S.brow, B.brow_ints * sizeof(int32_t));
+    ensure(S.dirs, B.dir_bytes);
+    ensure(S.out, B.out_bytes + BUFFER_SLACK);
+    ensure(S.align, B.count * sizeof(PairAlign));
+    ensure(S.pen, B.count * sizeof(int32_t));
+    ensure(S.cost, B.count * sizeof(int32_t));
+    ensure(S.counter, sizeof(uint32_t));
+    // ---- build descriptors in pinned staging
+    const size_t pairs_bytes = round_up(B.count * sizeof(PairDesc), 256);
+    const size_t tasks_bytes = round_up((size_t)B.nstrips * sizeof(StripTask), 256);
+    const size_t slots_bytes = round_up(B.count * sizeof(uint32_t), 256);
+    ensure_stage(S, pairs_bytes + tasks_bytes + slots_bytes);
+    if (S.staged_pending) {
+      SEQALK_CUDA(cudaEventSynchronize(S.staged));
+      S.staged_pending = false;
+    }
+    PairDesc *hp = reinterpret_cast<PairDesc *>(S.h_stage);
+    StripTask *ht = reinterpret_cast<StripTask *>(static_cast<uint8_t *>(S.h_stage) + pairs_bytes);
+    uint32_t *hs = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(S.h_stage) + pairs_bytes + tasks_bytes);
+    uint64_t dir_off = 0, brow_off = 0, out_off = 0;
+    uint32_t strip0 = 0;
+    int max_strips = 0;
+    for (size_t p = 0; p < B.count; ++p) {
+      const TaskIJ &tk = tasks_[B.first + p];
+      PairDesc d;
+      d.x_off = pack_->off[tk.i];
+      d.y_off = pack_->off[tk.j];
+      d.m = pack_->len[tk.i];
+      d.n = pack_->len[tk.j];
+      d.dir_off = dir_off;
+      d.brow_off = brow_off;
+      d.out_off = out_off;
+      d.strip0 = strip0;
+      d.nstrips = num_strips(d.m, R);
+      d.cap = (uint32_t)round_up((size_t)d.m + d.n, 16);
+      d.task_id = (int32_t)(B.first + p);
+      hp[p] = d;
+      hs[p] = result_slots_.empty() ? (uint32_t)(B.first + p) : result_slots_[B.first + p];
+      dir_off += (uint64_t)d.nstrips * strip_dir_bytes(d.n, R);
+      brow_off += 4ull * (uint64_t)macro_cols(d.n) + 4;
+      out_off += 2ull * d.cap;
+      strip0 += (uint32_t)d.nstrips;
+      max_strips = std::max(max_strips, d.nstrips);
+    }
+    // strip queue ordered (strip, pair): a strip's predecessor is always claimed earlier
+    {
+      size_t w = 0;
+      for (int s = 0; s < max_strips; ++s)
+        for (size_t p = 0; p < B.count; ++p)
+          if (s < hp[p].nstrips) ht[w++] = StripTask{(uint32_t)p, (uint32_t)s};
+    }
+    S.last_pairs.assign(hp, hp + B.count);
+    // ---- enqueue
+    cudaStream_t st = S.stream;
+    SEQALK_CUDA(cudaMemcpyAsync(S.pairs.p, hp, B.count * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+    SEQALK_CUDA(cudaMemcpyAsync(S.tasks.p, ht, (size_t)B.nstrips * sizeof(StripTask), cudaMemcpyHostToDevice, st));
+    SEQALK_CUDA(cudaMemcpyAsync(S.slots.p, hs, B.count * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SEQALK_CUDA(cudaEventRecord(S.staged, st));
+    S.staged_pending = true;
+    SEQALK_CUDA(cudaMemsetAsync(S.counter.p, 0, sizeof(uint32_t), st));
+    SEQALK_CUDA(cudaMemsetAsync(S.progress.p, 0, (size_t)B.nstrips * sizeof(uint32_t), st));
+
+    FillArgs fa;
+    fa.seq = static_cast<const uint8_t *>(seq_.p);
+    fa.pairs = static_cast<const PairDesc *>(S.pairs.p);
+    fa.tasks = static_cast<const StripTask *>(S.tasks.p);
+    fa.ntasks = B.nstrips;
+    fa.counter = static_cast<uint32_t *>(S.counter.p);
+    fa.progress = static_cast<uint32_t *>(S.progress.p);
+    fa.brow = static_cast<int32_t *>(S.brow.p);
+    fa.dirs = static_cast<uint8_t *>(S.dirs.p);
+    fa.penalties = static_cast<int32_t *>(S.pen.p);
+    fa.pxy = pxy_;
+    fa.pgap = pgap_;
+    SEQALK_CUDA(cudaEventRecord(ev_[4 * b + 0], st));
+    SEQALK_CUDA(launch_fill(fa, general_, sm_count_, st));
+    SEQALK_CUDA(cudaEventRecord(ev_[4 * b + 1], st));
+
+    TracebackArgs ta;
+    ta.seq = fa.seq;
+    ta.pairs = fa.pairs;
+    ta.npairs = (uint32_t)B.count;
+    ta.dirs = fa.dirs;
+    ta.out = static_cast<uint8_t *>(S.out.p);
+    ta.align = static_cast<PairAlign *>(S.align.p);
+    ta.path_cost = static_cast<int32_t *>(S.cost.p);
+    ta.pxy = pxy_;
+    ta.pgap = pgap_;
+    SEQALK_CUDA(launch_traceback(ta, st));
+    SEQALK_CUDA(cudaEventRecord(ev_[4 * b + 2], st));
+
+    DigestArgs da;
+    da.pairs = fa.pairs;
+    da.npairs = (uint32_t)B.count;
+    da.out = ta.out;
+    da.align = ta.align;
+    da.penalties = fa.penalties;
+    da.path_cost = ta.path_cost;
+    da.result_slot = static_cast<const uint32_t *>(S.slots.p);
+    da.digests = digests_dev;
+    da.penalties_out = penalties_dev;
+    da.error_flag = static_cast<uint32_t *>(err_.p);
+    SEQALK_CUDA(launch_digest(da, st));
+    SEQALK_CUDA(cudaEventRecord(ev_[4 * b + 3], st));
+    stats_.fill_launches++;
+    stats_.traceback_launches++;
+    stats_.digest_launches++;
+  }
+  for (Slot &S : slots_) SEQALK_CUDA(cudaStreamSynchronize(S.stream));
+  for (Slot &S : slots_) S.staged_pending = false;
+  uint32_t err = 0;
+  SEQALK_CUDA(cudaMemcpy(&err, err_.p, sizeof err, cudaMemcpyDeviceToHost));
+  if (err)
+    throw std::runtime_error("internal check failed: traceback path cost != dp[m][n] for at least one pair");
+  stats_.fill_ms = stats_.traceback_ms = stats_.digest_ms = 0;
+  for (size_t b = 0; b < batches_.size(); ++b) {
+    float ms = 0;
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[4 * b + 0], ev_[4 * b + 1]));
+    stats_.fill_ms += ms;
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[4 * b + 1], ev_[4 * b + 2]));
+    stats_.traceback_ms += ms;
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[4 * b + 2], ev_[4 * b + 3]));
+    stats_.digest_ms += ms;
+  }
+  stats_.wall_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+}
+
+void DeviceWorker::fetch(int32_t *penalties_host, uint8_t *digests_host) {
+  SEQALK_CUDA(cudaSetDevice(dev_));
+  const size_t T = tasks_.size();
+  if (!T) return;
+  if (penalties_host)
+    SEQALK_CUDA(cudaMemcpy(penalties_host, res_pen_.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (digests_host) SEQALK_CUDA(cudaMemcpy(digests_host, res_dig_.p, T * 64, cudaMemcpyDeviceToHost));
+}
+
+bool DeviceWorker::fetch_alignment(size_t index_in_job, std::vector<uint8_t> &a1, std::vector<uint8_t> &a2) {
+  SEQALK_CUDA(cudaSetDevice(dev_));
+  if (batches_.empty()) return false;
+  const size_t b = batches_.size() - 1;
+  const Batch &B = batches_[b];
+  if (index_in_job < B.first || index_in_job >= B.first + B.count) return false;
+  Slot &S = slots_[b % nslots_];
+  const size_t p = index_in_job - B.first;
+  const PairDesc &d = S.last_pairs[p];
+  PairAlign al;
+  SEQALK_CUDA(cudaMemcpy(&al, static_cast<PairAlign *>(S.align.p) + p, sizeof al, cudaMemcpyDeviceToHost));
+  a1.resize(al.len);
+  a2.resize(al.len);
+  const uint8_t *out = static_cast<const uint8_t *>(S.out.p);
+  if (al.len) {
+    SEQALK_CUDA(cudaMemcpy(a1.data(), out + d.out_off + al.start, al.len, cudaMemcpyDeviceToHost));
+    SEQALK_CUDA(cudaMemcpy(a2.data(), out + d.out_off + d.cap + al.start, al.len, cudaMemcpyDeviceToHost));
+  }
+  return true;
+}
+
+}  // namespace seqalk

@@ -1,0 +1,124 @@
+// engine.h — host-side orchestration of the all-pairs alignment on one GPU (internal).
+//
+// Plays the role of the reference's worker loop (recv Triple -> do_task -> send Packet,
+// submit/xuliny-seqalkway.cpp:342-357, 399-411) for one device: takes a list of (i, j)
+// tasks, cuts it into batches that fit the HBM budget for packed directions, and for each
+// batch runs  fill -> traceback -> digest  on one of NSLOT streams so that the latency-bound
+// traceback of batch b overlaps the fill of batch b+1.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "seqalk_kernels.h"
+
+namespace seqalk {
+
+// Host copy of the input in the layout the kernels read: every sequence starts on a
+// 16 B boundary and is followed by >= 16 zero bytes (the fill reads y in 4-byte words).
+struct SeqPack {
+  std::vector<uint8_t> bytes;
+  std::vector<uint32_t> off;
+  std::vector<int32_t> len;
+  int k = 0;
+  void build(const char *const *seqs, const int32_t *lens, int k);
+};
+
+struct TaskIJ {
+  int32_t i, j;  // x = seq[i] (rows), y = seq[j] (columns)
+};
+
+struct JobStats {
+  uint64_t cells = 0;          // sum of m*n over the job's tasks
+  uint64_t dir_bytes = 0;      // packed direction bytes written
+  uint32_t batches = 0;
+  uint32_t fill_launches = 0, traceback_launches = 0, digest_launches = 0;
+  double fill_ms = 0;          // sum of CUDA-event durations of the fill launches
+  double traceback_ms = 0, digest_ms = 0;
+  double wall_ms = 0;          // host wall time of run()
+};
+
+class DeviceWorker {
+ public:
+  explicit DeviceWorker(int device);
+  ~DeviceWorker();
+  DeviceWorker(const DeviceWorker &) = delete;
+  DeviceWorker &operator=(const DeviceWorker &) = delete;
+
+  int device() const { return dev_; }
+  // H2D of the packed sequences (kept resident until the next load()).
+  void load(const SeqPack &pack);
+  // Plans batches for `tasks`; result slot of tasks[t] is t unless result_slots is given.
+  void plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
+            const std::vector<uint32_t> *result_slots = nullptr);
+  // Runs every batch.  Results are written to (penalties_dev[slot], digests_dev[64*slot]);
+  // both may be null (-> worker-owned device arrays, read back with fetch()) or point
+  // into another GPU's memory when peer access is enabled (fused gather over NVLink).
+  void run(int32_t *penalties_dev = nullptr, uint8_t *digests_dev = nullptr);
+  // D2H of worker-owned results.
+  void fetch(int32_t *penalties_host, uint8_t *digests_host);
+  // Alignment strings of the LAST batch's pair `index_in_job` (only valid when the job is
+  // a single batch; used by seqalk_pair).  Returns false if not available.
+  bool fetch_alignment(size_t index_in_job, std::vector<uint8_t> &a1, std::vector<uint8_t> &a2);
+
+  const JobStats &stats() const { return stats_; }
+  size_t num_tasks() const { return tasks_.size(); }
+
+ private:
+  struct Batch {
+    size_t first, count;
+    uint64_t dir_bytes, brow_ints, out_bytes;
+    uint32_t nstrips;
+  };
+  struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+  };
+  struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf pairs, tasks, slots, progress, brow, dirs, out, align, pen, cost, counter;
+    void *h_stage = nullptr;  // pinned staging: pairs | tasks | slots
+    size_t h_cap = 0;
+    cudaEvent_t staged = nullptr;  // H2D of the staging buffer finished
+    bool staged_pending = false;
+    std::vector<PairDesc> last_pairs;  // descriptors of the last batch run on this slot
+  };
+  void ensure(DevBuf &b, size_t bytes);
+  void ensure_stage(Slot &s, size_t bytes);
+  void release(DevBuf &b);
+
+  int dev_;
+  int sm_count_ = 0;
+  size_t dir_budget_ = 0;
+  int nslots_ = 2;
+  std::vector<Slot> slots_;
+  DevBuf seq_;
+  const SeqPack *pack_ = nullptr;
+  SeqPack pack_copy_;
+  std::vector<TaskIJ> tasks_;
+  std::vector<uint32_t> result_slots_;
+  std::vector<Batch> batches_;
+  int pxy_ = 0, pgap_ = 0;
+  bool general_ = false;
+  DevBuf res_pen_, res_dig_, err_;
+  std::vector<cudaEvent_t> ev_;
+  JobStats stats_;
+};
+
+// cells = sum over tasks of len[i]*len[j] (64-bit; testing9/test.cpp:219 overflowed here)
+uint64_t total_cells(const SeqPack &pack, const std::vector<TaskIJ> &tasks);
+
+// The reference's task order (submit/xuliny-seqalkway.cpp:282-287).
+void all_tasks(int k, std::vector<TaskIJ> &out);
+inline int64_t task_id_of(int i, int j) { return (int64_t)i * (i - 1) / 2 + j; }
+void task_from_id(int64_t id, int32_t *i, int32_t *j);
+
+// Cell-balanced shard of tasks [id_begin, id_end) over nranks (LPT: largest first onto
+// the least loaded rank, ties by rank index), each rank's list returned in id order.
+void partition_lpt(const int32_t *lens, int k, int64_t id_begin, int64_t id_end, int nranks,
+                   std::vector<std::vector<int64_t>> &per_rank);
+
+void throw_cuda(cudaError_t e, const char *what, const char *file, int line);
+#define SEQALK_CUDA(x) ::seqalk::throw_cuda((x), #x, __FILE__, __LINE__)
+
+}  // namespace seqalk

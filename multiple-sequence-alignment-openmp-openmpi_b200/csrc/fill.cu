@@ -1,0 +1,275 @@
+// fill.cu — integer DP matrix fill, hand-written for sm_100a.
+//
+// Replaces the reference's OpenMP tile-wavefront fill
+//   submit/xuliny-seqalkway.cpp:435-491 (getMinimumPenalty2: init, tiling, recurrence :478-487)
+// and its sequential twin :584-609 (getMinimumPenalty).
+//
+// Work decomposition ("strip wavefront"):
+//   * a pair's DP matrix is cut into strips of 32*R rows; one warp sweeps one strip
+//     left to right; lane t owns R consecutive rows and trails lane t-1 by one macro
+//     column (4 DP columns), i.e. the warp is an anti-diagonal wavefront of R x 4 blocks;
+//   * the value crossing from lane t-1's bottom row to lane t's top row travels by
+//     __shfl_up_sync (4 per macro step), and so does the 4-byte word of y;
+//   * strip s hands its bottom row to strip s+1 through a per-pair boundary-row
+//     buffer (L2 resident) plus a per-strip progress counter (release/acquire), so
+//     consecutive strips of one pair run concurrently on different warps / CTAs /
+//     SMs as a second-level wavefront ("CTA wavefront" for long sequences), while
+//     a batch with many pairs degenerates to independent warps ("warp per pair");
+//   * strips are claimed from a global queue ordered (strip index, pair): every
+//     strip's predecessor is claimed earlier, by a warp that is already running,
+//     so the waits cannot deadlock and no cooperative launch is needed;
+//   * scores stay in registers in a gap-shifted domain H'[i][j] = H[i][j] - (i+j)*pgap,
+//     which makes all boundaries 0 and both gap moves free of adds:
+//         H'[i][j] = match ? H'[i-1][j-1] - 2*pgap
+//                          : min(H'[i-1][j-1] + pxy - 2*pgap, H'[i-1][j], H'[i][j-1])
+//     (comparisons are shift-invariant, so ties break exactly as in the reference);
+//   * per cell a 2-bit code is emitted: bit0 = "not diagonal", bit1 = "left strictly
+//     better than up".  The traceback reads DIAG if !bit0, else LEFT if bit1, else UP —
+//     the reference's priority order (match, mismatch-diag, up, left; :502-531).
+//     128 bits per lane are accumulated in registers and written with one 16 B store;
+//     a warp's store is one contiguous 512 B segment (strip-major, step-skewed layout).
+#include "seqalk_kernels.h"
+
+namespace seqalk {
+
+constexpr int FILL_THREADS = 128;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One lane's R x 4 block.  h[r] = H' of row r at the previous column; dg = H' of the row
+// above the block at the previous column; up_in[c] = H' of the row above at column c.
+//
+// Per cell, fast path (pxy >= 0, pgap >= 0, scores far from int32 overflow):
+//     t  = diag + B;  if (x == y) t = diag + A        ISETP + 2 adds
+//     v  = min3(up, left, t)                           VIMNMX3
+//     d1 = v - t      (< 0  <=>  diagonal not optimal) add
+//     d2 = left - up  (< 0  <=>  left strictly better) add
+//     bits = (bits << 1 | sign(d1)) << 1 | sign(d2)    2 funnel shifts (SHF.L.W)
+// On a match the reference takes the diagonal unconditionally (:478-479); with
+// non-negative penalties H[i-1][j-1] <= min(H[i-1][j], H[i][j-1]) + pgap, so the
+// plain minimum selects the same value and sign(d1) = 0 (DIAG) — identical output.
+// GENERAL (any integers): explicit select on match, compares instead of sign tricks.
+template <int R, bool GENERAL, bool CAPTURE>
+__device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)[R], const int (&up_in)[4],
+                                           unsigned yword, int A, int B, int (&outv)[4],
+                                           unsigned (&bits)[R / 4], int cn, int rm, int &captured) {
+#pragma unroll
+  for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int yc = (int)((yword >> (8 * c)) & 0xffu);
+    int diag = dg;
+    int up = up_in[c];
+    dg = up;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int w = (c * R + r) / CELLS_PER_WORD;  // cells are shifted in, first cell ends up highest
+      const int left = h[r];
+      int v;
+      if (!GENERAL) {
+        int t = diag + B;
+        asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p add.s32 %0, %3, %4;}"
+            : "+r"(t)
+            : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A));
+        v = min(min(up, left), t);
+        const int d1 = v - t;
+        const int d2 = left - up;
+        bits[w] = __funnelshift_l((unsigned)d1, bits[w], 1);
+        bits[w] = __funnelshift_l((unsigned)d2, bits[w], 1);
+      } else {
+        const bool match = (xc[r] == yc);
+        const int t = diag + B;
+        const int m1 = min(up, left);
+        v = match ? diag + A : min(t, m1);
+        const unsigned nd = ((!match) && (t > m1)) ? 2u : 0u;
+        const unsigned lf = (up > left) ? 1u : 0u;
+        bits[w] = (bits[w] << 2) | nd | lf;
+      }
+      diag = left;
+      up = v;
+      h[r] = v;
+    }
+    outv[c] = up;
+    if (CAPTURE) {
+      // H'[m][n]: row register rm after column cn (later columns of this block are padding)
+      if (c == cn) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r == rm) captured = h[r];
+      }
+    }
+  }
+}
+
+template <int R, bool GENERAL>
+__device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc &P, const int pair_index,
+                                              const int s, const int lane) {
+  constexpr int G = 16 / R;  // macro steps per 16 B direction store
+  const unsigned FULL = 0xffffffffu;
+  const int m = P.m, n = P.n;
+  const int nq = (n + 3) >> 2;
+  const int ngroups = (nq + 31 + G - 1) / G;
+  const int A = -2 * a.pgap, B = a.pxy - 2 * a.pgap;
+  const bool first = (s == 0), last = (s == P.nstrips - 1);
+
+  const uint8_t *__restrict__ xs = a.seq + P.x_off;
+  const uint8_t *__restrict__ ys = a.seq + P.y_off;
+  int4 *__restrict__ brow = reinterpret_cast<int4 *>(a.brow + P.brow_off);
+  uint4 *__restrict__ dout =
+      reinterpret_cast<uint4 *>(a.dirs + P.dir_off + (uint64_t)s * ((uint64_t)ngroups * 512ull)) + lane;
+  const unsigned *prev_progress = a.progress + P.strip0 + (first ? 0 : s - 1);
+  unsigned *my_progress = a.progress + P.strip0 + s;
+
+  // this lane's rows
+  const int row0 = s * (32 * R) + lane * R;
+  int xc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) xc[r] = (row0 + r < m) ? (int)xs[row0 + r] : (0x100 + r);
+
+  // penalty capture: cell (m, n) lives in lane tm, register rm, macro col nq-1, column cn
+  const int tm = ((m - 1) % (32 * R)) / R, rm = (m - 1) % R, cn = (n - 1) & 3;
+
+  int h[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) h[r] = 0;
+  int dg = 0;
+  int outv[4] = {0, 0, 0, 0};
+  unsigned yw = 0;
+
+  // lane 0's software pipeline: boundary values + y words of the NEXT group
+  int4 top_next[G];
+  unsigned y_next[G];
+  int avail = first ? nq : 0;  // macro cols of the predecessor's bottom row known to be published
+
+  auto fetch_group = [&](int g, int4(&top)[G], unsigned(&yy)[G]) {
+    // make sure the predecessor strip has published macro cols [g*G, g*G+G)
+    const int need = min(nq, g * G + G);
+    if (avail < need) {
+      for (;;) {
+        unsigned v = 0;
+        if (lane == 0) v = ld_acquire_u32(prev_progress);
+        v = __shfl_sync(FULL, v, 0);
+        avail = (int)v;
+        if (avail >= need) break;
+        __nanosleep(64);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int qc = g * G + u;
+      top[u] = make_int4(0, 0, 0, 0);
+      yy[u] = 0u;
+      if (lane == 0 && qc < nq) {
+        yy[u] = __ldg(reinterpret_cast<const unsigned *>(ys) + qc);
+        if (!first) top[u] = __ldcg(brow + qc);
+      }
+    }
+  };
+
+  fetch_group(0, top_next, y_next);
+
+  for (int g = 0; g < ngroups; ++g) {
+    int4 top_cur[G];
+    unsigned y_cur[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      top_cur[u] = top_next[u];
+      y_cur[u] = y_next[u];
+    }
+    if ((g + 1) * G < nq) fetch_group(g + 1, top_next, y_next);
+
+    unsigned pk[4];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int q = g * G + u;
+      int up_in[4];
+      up_in[0] = __shfl_up_sync(FULL, outv[0], 1);
+      up_in[1] = __shfl_up_sync(FULL, outv[1], 1);
+      up_in[2] = __shfl_up_sync(FULL, outv[2], 1);
+      up_in[3] = __shfl_up_sync(FULL, outv[3], 1);
+      unsigned ny = __shfl_up_sync(FULL, yw, 1);
+      if (lane == 0) {
+        up_in[0] = top_cur[u].x;
+        up_in[1] = top_cur[u].y;
+        up_in[2] = top_cur[u].z;
+        up_in[3] = top_cur[u].w;
+        ny = y_cur[u];
+      }
+      const int qc = q - lane;  // this lane's macro column
+      unsigned bits[R / 4];
+#pragma unroll
+      for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
+      if (qc >= 0 && qc < nq) {
+        yw = ny;
+        int cap = 0;
+        if (last && q - tm == nq - 1) {  // warp-uniform, once per pair
+          macro_step<R, GENERAL, true>(h, dg, xc, up_in, yw, A, B, outv, bits, cn, rm, cap);
+          if (lane == tm) a.penalties[pair_index] = cap + (m + n) * a.pgap;
+        } else {
+          macro_step<R, GENERAL, false>(h, dg, xc, up_in, yw, A, B, outv, bits, cn, rm, cap);
+        }
+        if (lane == 31 && !last) brow[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
+      }
+#pragma unroll
+      for (int w = 0; w < R / 4; ++w) pk[u * (R / 4) + w] = bits[w];
+    }
+    dout[(size_t)g * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+
+    // publish progress of the bottom row (lane 31 trails by 31 macro steps)
+    if (!last) {
+      const int done = min(nq, (g + 1) * G - 31);
+      const int prev_done = min(nq, g * G - 31);
+      if (done > 0 && ((done / PUBLISH_EVERY) != (max(prev_done, 0) / PUBLISH_EVERY) || done == nq) &&
+          done != prev_done) {
+        if (lane == 31) st_release_u32(my_progress, (unsigned)done);
+      }
+    }
+  }
+}
+
+template <int R, bool GENERAL>
+__global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillArgs a) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(a.counter, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.ntasks) break;
+    const StripTask task = a.tasks[t];
+    const PairDesc P = a.pairs[task.pair];
+    process_strip<R, GENERAL>(a, P, (int)task.pair, (int)task.strip, lane);
+  }
+}
+
+int fill_blocks_per_sm(bool general) {
+  int nb = 0;
+  if (general)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_kernel<FILL_R, true>, FILL_THREADS, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_kernel<FILL_R, false>, FILL_THREADS, 0);
+  return nb;
+}
+
+cudaError_t launch_fill(const FillArgs &args, bool general, int sm_count, cudaStream_t stream) {
+  if (args.ntasks == 0) return cudaSuccess;
+  int nb = fill_blocks_per_sm(general);
+  if (nb < 1) return cudaErrorLaunchOutOfResources;
+  // persistent grid: every SM full, but no more warps than strips
+  long long want = ((long long)args.ntasks + (FILL_THREADS / 32) - 1) / (FILL_THREADS / 32);
+  long long grid = (long long)sm_count * nb;
+  if (grid > want) grid = want;
+  if (general)
+    fill_kernel<FILL_R, true><<<(unsigned)grid, FILL_THREADS, 0, stream>>>(args);
+  else
+    fill_kernel<FILL_R, false><<<(unsigned)grid, FILL_THREADS, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace seqalk

@@ -1,0 +1,117 @@
+// traceback.cu — walks the packed 2-bit direction matrix on the GPU and writes the two
+// gapped alignment strings.
+//
+// Replaces the reference's serial traceback + tail fill + strip scan:
+//   submit/xuliny-seqalkway.cpp:502-531 (traceback, priority match / mismatch-diag / up / left),
+//   :535-558 (tails: leftover prefix against '_'), :191-214 (do_task: strip common '_' pad,
+//   build align1/align2).
+//
+// Closed form used here: with the walk stopping at (i, j), one of
+// them 0,   align1 = x[0:i] + '_'*j + path_x,   align2 = '_'*i + y[0:j] + path_y,
+// written right-aligned into two per-pair byte buffers so that both strings end at
+// offset m+n; `start` marks their first byte.
+//
+// One thread per pair: the walk is a dependent chain of <= m+n steps; pairs of a batch
+// run in parallel.  The thread caches the last 32-bit direction word (16 cells = a lane's
+// 8 rows x 2 columns for R = 8), and emits output through 8-byte registers so that the
+// stores are 64-bit, not per character.
+#include "seqalk_kernels.h"
+
+namespace seqalk {
+
+// Accumulates bytes written right-to-left and flushes aligned 8-byte words.
+struct BackWriter {
+  uint8_t *base;   // buffer base (16 B aligned)
+  uint32_t pos;    // next byte goes to base[pos-1]
+  uint64_t acc;    // bytes for the 8-byte word containing pos-1 (little endian placement)
+  __device__ __forceinline__ void init(uint8_t *b, uint32_t end) {
+    base = b;
+    pos = end;
+    acc = 0;
+  }
+  __device__ __forceinline__ void put(uint8_t ch) {
+    --pos;
+    acc |= (uint64_t)ch << (8 * (pos & 7));
+    if ((pos & 7) == 0) {
+      *reinterpret_cast<uint64_t *>(base + pos) = acc;
+      acc = 0;
+    }
+  }
+  // flush the partial word (bytes below pos inside the word are written as 0; they are
+  // before `start`, nobody reads them)
+  __device__ __forceinline__ void finish() {
+    if (pos & 7) *reinterpret_cast<uint64_t *>(base + (pos & ~7u)) = acc;
+  }
+};
+
+template <int R>
+__global__ void __launch_bounds__(TRACEBACK_THREADS) traceback_kernel(const TracebackArgs a) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.npairs) return;
+  const PairDesc P = a.pairs[p];
+  const int m = P.m, n = P.n;
+  const uint8_t *__restrict__ xs = a.seq + P.x_off;
+  const uint8_t *__restrict__ ys = a.seq + P.y_off;
+  const uint8_t *__restrict__ dirs = a.dirs + P.dir_off;
+  BackWriter w1, w2;
+  w1.init(a.out + P.out_off, (uint32_t)(m + n));
+  w2.init(a.out + P.out_off + P.cap, (uint32_t)(m + n));
+
+  int i = m, j = n;
+  long long cost = 0;  // path cost, must equal dp[m][n] (checked on the host)
+  uint64_t cached_off = ~0ull;
+  uint32_t cached = 0;
+  while (i > 0 && j > 0) {
+    const DirAddr da = dir_addr(i, j, n, R);
+    if (da.byte_off != cached_off) {
+      cached_off = da.byte_off;
+      cached = __ldcg(reinterpret_cast<const uint32_t *>(dirs + da.byte_off));
+    }
+    const uint32_t code = (cached >> da.shift) & 3u;
+    const uint8_t xch = xs[i - 1], ych = ys[j - 1];
+    if (!(code & DIR_NOT_DIAG)) {
+      w1.put(xch);
+      w2.put(ych);
+      cost += (xch == ych) ? 0 : a.pxy;
+      --i;
+      --j;
+    } else if (!(code & DIR_LEFT_BETTER)) {  // up: consume x, gap in y
+      w1.put(xch);
+      w2.put('_');
+      cost += a.pgap;
+      --i;
+    } else {  // left: gap in x, consume y
+      w1.put('_');
+      w2.put(ych);
+      cost += a.pgap;
+      --j;
+    }
+  }
+  // tails: only one of i, j is non-zero
+  cost += (long long)(i + j) * a.pgap;
+  for (; i > 0; --i) {
+    w1.put(xs[i - 1]);
+    w2.put('_');
+  }
+  for (; j > 0; --j) {
+    w1.put('_');
+    w2.put(ys[j - 1]);
+  }
+  const uint32_t start = w1.pos;
+  w1.finish();
+  w2.finish();
+  PairAlign r;
+  r.start = start;
+  r.len = (uint32_t)(m + n) - start;
+  a.align[p] = r;
+  a.path_cost[p] = (int32_t)cost;
+}
+
+cudaError_t launch_traceback(const TracebackArgs &args, cudaStream_t stream) {
+  if (args.npairs == 0) return cudaSuccess;
+  const unsigned grid = (args.npairs + TRACEBACK_THREADS - 1) / TRACEBACK_THREADS;
+  traceback_kernel<FILL_R><<<grid, TRACEBACK_THREADS, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace seqalk

@@ -1,0 +1,176 @@
+"""One process per GPU: the reference's master/worker task farm re-shaped for NVLink.
+
+Reference (submit/xuliny-seqalkway.cpp): rank 0 broadcasts the inputs (:249-266), hands out
+Triple{i,j,id} tasks one by one (:280-331), workers return Packet{penalty,id,hash} (:342-357,
+:399-411), rank 0 folds the hashes in id order (:334-337).
+
+Here: every rank holds the inputs (replicated, as in the reference), the k(k-1)/2 tasks are
+sharded statically by cell count (LPT — independent units, no data-path collective during the
+fill), every rank runs its shard on its own GPU through the C ABI, and the per-task
+(penalty, 64-byte digest) records are gathered over NCCL/NVLink with one all_gather per chunk
+of task ids.  Rank 0 scatters them back into the reference's task order and folds the chain;
+with ``nchunks > 1`` the fold of chunk c overlaps the GPUs' work on chunk c+1.
+
+``compute`` is injectable so that the shard/gather/reorder logic is testable on CPU with the
+gloo backend (tests/test_distributed_cpu.py); the default computes on the rank's GPU and
+fails loudly without one.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import Job, fold_chain, partition_all
+
+ComputeFn = Callable[[Sequence[bytes], int, int, np.ndarray], Tuple[np.ndarray, np.ndarray]]
+
+
+class ShardPlan:
+    """Chunks of task ids x ranks.  chunk c covers ids [bounds[c], bounds[c+1])."""
+
+    def __init__(self, lens: Sequence[int], world: int, nchunks: int = 1):
+        k = len(lens)
+        T = k * (k - 1) // 2
+        nchunks = max(1, min(nchunks, max(T, 1)))
+        self.T, self.world = T, world
+        self.bounds = [T * c // nchunks for c in range(nchunks + 1)]
+        self.ids: List[List[np.ndarray]] = [
+            partition_all(lens, world, self.bounds[c], self.bounds[c + 1]) for c in range(nchunks)]
+
+    @property
+    def nchunks(self) -> int:
+        return len(self.ids)
+
+    def rank_ids(self, rank: int) -> np.ndarray:
+        """All ids of a rank, chunk after chunk (each chunk increasing)."""
+        parts = [self.ids[c][rank] for c in range(self.nchunks)]
+        return np.concatenate(parts) if parts else np.zeros(0, np.int64)
+
+    def max_count(self, c: int) -> int:
+        return max((len(a) for a in self.ids[c]), default=0)
+
+
+class GpuShard:
+    """A rank's tasks resident on its GPU: one Job per chunk, results into torch tensors."""
+
+    def __init__(self, genes: Sequence[bytes], pxy: int, pgap: int, plan: ShardPlan, rank: int, device: int):
+        import torch
+
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.plan, self.rank = plan, rank
+        self.jobs = [Job(genes, pxy, pgap, plan.ids[c][rank], device=device) for c in range(plan.nchunks)]
+        # gather buffers: [penalty int32 | 64 digest bytes] = 68 bytes per task, padded to the
+        # largest shard of the chunk so that one all_gather_into_tensor moves everything
+        self.send = [torch.zeros((max(plan.max_count(c), 1), 68), dtype=torch.uint8, device=self.device)
+                     for c in range(plan.nchunks)]
+        self.pen = [torch.zeros(max(len(plan.ids[c][rank]), 1), dtype=torch.int32, device=self.device)
+                    for c in range(plan.nchunks)]
+        self.dig = [torch.zeros((max(len(plan.ids[c][rank]), 1), 64), dtype=torch.uint8, device=self.device)
+                    for c in range(plan.nchunks)]
+
+    def run_chunk(self, c: int):
+        """fill + traceback + digest of this rank's tasks of chunk c; returns the send buffer."""
+        n = len(self.plan.ids[c][self.rank])
+        if n:
+            self.jobs[c].run(self.pen[c].data_ptr(), self.dig[c].data_ptr())
+            self.send[c][:n, :4] = self.pen[c][:n].view(self.torch.uint8).view(n, 4)
+            self.send[c][:n, 4:] = self.dig[c][:n]
+        return self.send[c]
+
+    def stats(self):
+        return [j.stats() for j in self.jobs]
+
+    def close(self):
+        for j in self.jobs:
+            j.close()
+
+
+def _scatter(plan: ShardPlan, c: int, gathered: np.ndarray, penalties: np.ndarray, digests: np.ndarray) -> None:
+    """gathered: (world, maxcount, 68) uint8 -> task-ordered arrays."""
+    for r in range(plan.world):
+        ids = plan.ids[c][r]
+        n = len(ids)
+        if n:
+            rec = gathered[r, :n]
+            penalties[ids] = rec[:, :4].copy().view(np.int32).reshape(n)
+            digests[ids] = rec[:, 4:]
+
+
+def run_sharded(plan: ShardPlan, rank: int, run_chunk: Callable[[int], "object"], group=None,
+                ) -> Optional[Tuple[str, np.ndarray]]:
+    """Drives the chunks: run, all_gather, and (rank 0) scatter + fold in task order.
+
+    ``run_chunk(c)`` returns a torch uint8 tensor (maxcount_c, 68) living on the device the
+    process group communicates on.  Returns (digest, penalties) on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    world = plan.world
+    penalties = np.zeros(plan.T, dtype=np.int32) if rank == 0 else None
+    digests = np.zeros((plan.T, 64), dtype=np.uint8) if rank == 0 else None
+    state = {"hex": ""}
+    folder: Optional[threading.Thread] = None
+
+    def fold_range(c: int, host: np.ndarray):
+        _scatter(plan, c, host, penalties, digests)
+        b, e = plan.bounds[c], plan.bounds[c + 1]
+        state["hex"] = fold_chain(digests[b:e], state["hex"])
+
+    for c in range(plan.nchunks):
+        send = run_chunk(c)
+        if world > 1:
+            rows = send.shape[0]
+            flat = torch.empty((world * rows, send.shape[1]), dtype=send.dtype, device=send.device)
+            dist.all_gather_into_tensor(flat, send.contiguous(), group=group)
+            recv = flat.view(world, rows, send.shape[1])
+        else:
+            recv = send.unsqueeze(0)
+        if rank == 0:
+            host = recv.cpu().numpy()  # D2H of the gathered records (synchronises the stream)
+            if folder is not None:
+                folder.join()
+            folder = threading.Thread(target=fold_range, args=(c, host))
+            folder.start()
+    if folder is not None:
+        folder.join()
+    if rank == 0:
+        return state["hex"], penalties
+    return None
+
+
+def all_pairs_distributed(genes: Sequence[bytes], pxy: int, pgap: int, *, nchunks: int = 1, group=None,
+                          device: Optional[int] = None, compute: Optional[ComputeFn] = None,
+                          ) -> Optional[Tuple[str, np.ndarray]]:
+    """getMinimumPenalties over all ranks of the default process group.
+
+    Every rank passes the same inputs.  Returns (digest, penalties) on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    lens = [len(g) for g in genes]
+    plan = ShardPlan(lens, world, nchunks)
+    if compute is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("all_pairs_distributed needs one B200 per rank (no CPU fallback)")
+        dev = torch.cuda.current_device() if device is None else device
+        shard = GpuShard(genes, pxy, pgap, plan, rank, dev)
+        try:
+            return run_sharded(plan, rank, shard.run_chunk, group)
+        finally:
+            shard.close()
+
+    def run_chunk(c: int):
+        ids = plan.ids[c][rank]
+        buf = np.zeros((max(plan.max_count(c), 1), 68), dtype=np.uint8)
+        if len(ids):
+            pen, dig = compute(genes, pxy, pgap, ids)
+            buf[:len(ids), :4] = np.asarray(pen, dtype=np.int32).view(np.uint8).reshape(-1, 4)
+            buf[:len(ids), 4:] = np.asarray(dig, dtype=np.uint8).reshape(-1, 64)
+        return torch.from_numpy(buf)
+
+    return run_sharded(plan, rank, run_chunk, group)

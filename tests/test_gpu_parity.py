@@ -1,0 +1,241 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the CPU oracle on the same
+inputs, against the reference's golden outputs, and — at sizes the oracle cannot reach in
+seconds — through size-independent properties.  Everything here is bit-exact (int32 / bytes)."""
+import hashlib
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init(seqalk):
+    seqalk.init(1)
+    yield
+
+
+def _check_all_pairs(seqalk, oracle, genes, pxy, pgap):
+    digest, pen = seqalk.get_minimum_penalties(genes, pxy, pgap)
+    od, op, oh = oracle.all_pairs(genes, pxy, pgap, want_pair_hashes=True)
+    if digest != od or not np.array_equal(pen, op):
+        # locate the first differing pair for the failure message
+        with seqalk.Job(genes, pxy, pgap) as job:
+            job.run()
+            jp, jd = job.fetch()
+        bad = [t for t in range(len(op)) if jp[t] != op[t] or jd[t].tobytes().hex() != oh[t]]
+        raise AssertionError(f"pxy={pxy} pgap={pgap} first bad task {bad[:5]} of {len(op)}; "
+                             f"lens={[len(g) for g in genes]}")
+
+
+# ---------------------------------------------------------------- golden vectors
+
+@pytest.mark.parametrize("name", ["mseq", "mseq1", "xulin_test", "xulin"])
+def test_golden_small(seqalk, load_fixture, name):
+    pxy, pgap, genes, e = load_fixture(name)
+    digest, pen = seqalk.get_minimum_penalties(genes, pxy, pgap)
+    assert list(pen) == e["penalties"]
+    assert digest == e["digest"]
+
+
+def test_golden_pair_hashes(seqalk, load_fixture):
+    pxy, pgap, genes, e = load_fixture("xulin_test")
+    with seqalk.Job(genes, pxy, pgap) as job:
+        job.run()
+        pen, dig = job.fetch()
+    assert [d.tobytes().hex() for d in dig] == e["pair_hashes"]
+    assert list(pen) == e["penalties"]
+    assert seqalk.fold_chain(dig) == e["digest"]
+
+
+@pytest.mark.parametrize("name", ["big13", "big13_2"])
+def test_golden_big13(seqalk, load_fixture, name):
+    """BASELINE config 2: 278.5 G cells, bit-exact digest vs the reference's CPU run."""
+    pxy, pgap, genes, e = load_fixture(name)
+    digest, pen = seqalk.get_minimum_penalties(genes, pxy, pgap)
+    assert list(pen) == e["penalties"]
+    assert digest == e["digest"]
+
+
+def test_driver_stdin_stdout_bytes(load_fixture, workloads):
+    """seqalkway: same stdout bytes as the reference main, except the time value."""
+    exe = os.path.join(ROOT, "multiple-sequence-alignment-openmp-openmpi_b200", "seqalkway")
+    for name in ["mseq", "mseq1"]:
+        pxy, pgap, genes, e = load_fixture(name)
+        raw = open(os.path.join(ROOT, "tests", "golden", e["file"]), "rb").read()
+        out = subprocess.run([exe], input=raw, stdout=subprocess.PIPE, check=True,
+                             env=dict(os.environ, SEQALK_GPUS="1")).stdout.decode()
+        lines = out.split("\n")
+        assert lines[0].startswith("Time: ") and lines[0].endswith(" us")
+        assert "\n".join(lines[1:]) == e["digest"] + "\n" + "".join(f"{p} " for p in e["penalties"]) + "\n"
+
+
+# ---------------------------------------------------------------- oracle parity, seeded
+
+def test_fuzz_small_vs_oracle(seqalk, oracle):
+    rnd = random.Random(99)
+    for it in range(60):
+        k = rnd.randint(2, 7)
+        alpha = rnd.choice([b"A", b"AC", b"ACGT", b"ACGTacgt", b"xyzXYZ09"])
+        genes = [bytes(rnd.choice(alpha) for _ in range(rnd.randint(1, 300))) for _ in range(k)]
+        pxy = rnd.choice([0, 1, 2, 3, 5, 9])
+        pgap = rnd.choice([0, 1, 2, 3, 7])
+        _check_all_pairs(seqalk, oracle, genes, pxy, pgap)
+
+
+def test_strip_and_macro_column_boundaries(seqalk, oracle):
+    """Lengths around the kernel's tiling: 8 rows per lane, 256 rows per strip, 4-column macro
+    columns, 16 B direction words."""
+    rnd = random.Random(7)
+    lens = [1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 255, 256, 257, 511, 512, 513, 767, 769, 1023, 1025]
+    genes = [bytes(rnd.choice(b"ACGT") for _ in range(L)) for L in lens]
+    _check_all_pairs(seqalk, oracle, genes, 3, 2)
+
+
+def test_general_kernel_negative_and_large_penalties(seqalk, oracle):
+    rnd = random.Random(3)
+    genes = [bytes(rnd.choice(b"ACG") for _ in range(rnd.randint(1, 400))) for _ in range(6)]
+    for pxy, pgap in [(-1, 2), (3, -1), (-2, -3), (0, 0), (1000000, 3), (2, 900000)]:
+        _check_all_pairs(seqalk, oracle, genes, pxy, pgap)
+
+
+def test_forced_general_kernel_equals_fast_kernel(seqalk, oracle, monkeypatch):
+    rnd = random.Random(4)
+    genes = [bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(200, 900))) for _ in range(6)]
+    d_fast, p_fast = seqalk.get_minimum_penalties(genes, 3, 2)
+    monkeypatch.setenv("SEQALK_FORCE_GENERAL", "1")
+    d_gen, p_gen = seqalk.get_minimum_penalties(genes, 3, 2)
+    assert d_fast == d_gen and np.array_equal(p_fast, p_gen)
+    od, op, _ = oracle.all_pairs(genes, 3, 2)
+    assert d_fast == od
+
+
+def test_special_shapes(seqalk, oracle):
+    base = bytes(random.Random(1).choice(b"ACGT") for _ in range(700))
+    cases = [
+        [base, base],                      # equal strings: pure diagonal
+        [base, base[100:400]],             # substring: long pure-gap runs (tested in big13)
+        [base[100:400], base],
+        [b"A" * 500, b"A" * 137],          # one-letter alphabet
+        [b"A" * 300, b"C" * 300],          # no match anywhere
+        [b"AcGt" * 50, b"ACGT" * 50],      # case-sensitive comparison
+        [b"G", b"G"], [b"G", b"T"], [b"G", base], [base, b"T"],
+        [bytes([200, 201, 250, 128] * 40), bytes([201, 200, 128, 250] * 37)],  # high bytes
+    ]
+    for genes in cases:
+        _check_all_pairs(seqalk, oracle, genes, 3, 2)
+        _check_all_pairs(seqalk, oracle, genes, 5, 1)
+
+
+def test_single_pair_arrays(seqalk, oracle):
+    """getMinimumPenalty: right-aligned int arrays, '_' pad, strip scan gives the strings."""
+    rnd = random.Random(12)
+    for _ in range(10):
+        x = bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(1, 600)))
+        y = bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(1, 600)))
+        pen, xans, yans = seqalk.get_minimum_penalty(x, y, 3, 2)
+        open_, a1, a2, _ = oracle.pair(x, y, 3, 2)
+        assert pen == open_
+        l, L = len(x) + len(y), len(a1)
+        assert bytes(int(v) for v in xans[l - L + 1:]) == a1
+        assert bytes(int(v) for v in yans[l - L + 1:]) == a2
+        assert np.all(xans[1:l - L + 1] == 95) and np.all(yans[1:l - L + 1] == 95)
+        assert seqalk.alignment_strings(xans, yans) == (a1, a2)
+    xa, ya = [0] * 12, [0] * 12
+    assert seqalk.getMinimumPenalty("AGGGCT", "AGGCA", 3, 2, xa, ya) == 5
+    pens = [0] * 3
+    assert seqalk.getMinimumPenalties(["AGGGCT", "AGGCA", "AAAGGGCT"], 3, 3, 2, pens).startswith("602d0f604e8f")
+    assert pens == [5, 4, 9]
+
+
+def test_batching_does_not_change_results(seqalk, oracle, workloads, monkeypatch):
+    genes = workloads.mixed(14, seed=5, lo=300, hi=2500)
+    d1, p1 = seqalk.get_minimum_penalties(genes, 3, 2)
+    with seqalk.Job(genes, 3, 2) as job:
+        job.run()
+        assert job.stats().batches == 1
+    monkeypatch.setenv("SEQALK_DIR_BUDGET_GB", "0.002")  # ~2 MB of directions per batch
+    with seqalk.Job(genes, 3, 2) as job:
+        job.run()
+        pen, dig = job.fetch()
+        st = job.stats()
+    assert st.batches > 5 and st.fill_launches == st.batches
+    assert st.cells == workloads.total_cells(genes)
+    assert seqalk.fold_chain(dig) == d1 and np.array_equal(pen, p1)
+    od, op, _ = oracle.all_pairs(genes, 3, 2)
+    assert d1 == od and np.array_equal(p1, op)
+
+
+def test_job_subset_and_device_pointers(seqalk, oracle, workloads):
+    import torch
+
+    genes = workloads.mixed(10, seed=8, lo=100, hi=1200)
+    od, op, oh = oracle.all_pairs(genes, 3, 2, want_pair_hashes=True)
+    ids = seqalk.partition([len(g) for g in genes], 3, 1)
+    pen_t = torch.zeros(len(ids), dtype=torch.int32, device="cuda")
+    dig_t = torch.zeros((len(ids), 64), dtype=torch.uint8, device="cuda")
+    with seqalk.Job(genes, 3, 2, ids, device=0) as job:
+        job.run(pen_t.data_ptr(), dig_t.data_ptr())
+    torch.cuda.synchronize()
+    assert pen_t.cpu().tolist() == [int(op[t]) for t in ids]
+    assert [bytes(r).hex() for r in dig_t.cpu().numpy()] == [oh[t] for t in ids]
+
+
+def test_distributed_single_rank_gpu(seqalk, oracle, workloads):
+    import importlib
+
+    dmod = importlib.import_module("multiple-sequence-alignment-openmp-openmpi_b200.distributed")
+    genes = workloads.mixed(12, seed=21, lo=100, hi=900)
+    digest, pen = dmod.all_pairs_distributed(genes, 3, 2, nchunks=3, device=0)
+    od, op, _ = oracle.all_pairs(genes, 3, 2)
+    assert digest == od and np.array_equal(pen, op)
+
+
+# ---------------------------------------------------------------- BASELINE shapes
+
+def test_cfg3_sample_vs_oracle(seqalk, oracle, workloads):
+    """Config 3 shape (10k x 10k, uniform ACGT): a 10-sequence prefix of the seeded input."""
+    genes = workloads.uniform(200, 10000, 200)[:10]
+    _check_all_pairs(seqalk, oracle, genes, 3, 2)
+
+
+def test_cfg4_sample_vs_oracle(seqalk, oracle, workloads):
+    """Config 4 shape (1k-20k mixed): seeded sample incl. the extremes of length ratio."""
+    genes = workloads.mixed(1000, 1000)
+    lens = [len(g) for g in genes]
+    order = np.argsort(lens)
+    pick = sorted(set(int(v) for v in list(order[:3]) + list(order[-3:]) + [0, 1, 2, 500]))
+    _check_all_pairs(seqalk, oracle, [genes[i] for i in pick], 3, 2)
+
+
+def _alignment_properties(x, y, pen, xans, yans, pxy, pgap, seqalk):
+    a1, a2 = seqalk.alignment_strings(xans, yans)
+    A1, A2 = np.frombuffer(a1, np.uint8), np.frombuffer(a2, np.uint8)
+    assert len(A1) == len(A2)
+    assert A1[A1 != 95].tobytes() == x and A2[A2 != 95].tobytes() == y
+    assert not np.any((A1 == 95) & (A2 == 95))
+    gaps = int(np.sum((A1 == 95) | (A2 == 95)))
+    mism = int(np.sum((A1 != 95) & (A2 != 95) & (A1 != A2)))
+    assert gaps * pgap + mism * pxy == pen           # the path costs exactly dp[m][n]
+    return hashlib.sha512((hashlib.sha512(a1).hexdigest() + hashlib.sha512(a2).hexdigest()).encode()).hexdigest()
+
+
+def test_cfg5_full_size_properties(seqalk, oracle, workloads):
+    """Config 5: one 200 000 x 200 000 pair (4e10 cells, 10 GB of packed directions).  The
+    oracle needs minutes for this, so: alignment strips back to x / y, its cost equals the
+    reported penalty, the device digest equals hashlib over the returned strings, the score is
+    symmetric, and a 20 000-column prefix problem matches the oracle's linear-memory score."""
+    x, y = workloads.uniform(2, 200000, 2)[::-1]  # task (1,0): x = genes[1], y = genes[0]
+    pen, xans, yans = seqalk.get_minimum_penalty(x, y, 3, 2)
+    ph = _alignment_properties(x, y, pen, xans, yans, 3, 2, seqalk)
+    digest, pens = seqalk.get_minimum_penalties([y, x], 3, 2)
+    assert pens[0] == pen
+    assert digest == hashlib.sha512(ph.encode()).hexdigest()
+    pen_t, _, _ = seqalk.get_minimum_penalty(y, x, 3, 2)
+    assert pen_t == pen
+    p2, _, _ = seqalk.get_minimum_penalty(x[:20000], y[:20000], 3, 2)
+    assert p2 == oracle.pair_score(x[:20000], y[:20000], 3, 2)
