@@ -229,6 +229,14 @@ int seqalk_all_pairs(const char *const *seqs, const int32_t *lens, int32_t k, in
     pack.build(seqs, lens, k);
     std::vector<TaskIJ> tasks;
     all_tasks(k, tasks);
+    if (r.workers.size() == 1) {
+      // one GPU: results stream back batch by batch, the chain is folded under the GPU's shadow
+      DeviceWorker &w = *r.workers[0];
+      w.load(pack);
+      w.plan(tasks, pxy, pgap);
+      w.run_and_fold(penalties_out, digest_hex_out);
+      return 0;
+    }
     std::vector<uint8_t> digests(tasks.size() * 64);
     run_tasks(r, pack, tasks, pxy, pgap, penalties_out, digests.data());
     size_t hl = 0;

@@ -1,5 +1,6 @@
 // engine.cu — see engine.h
 #include "engine.h"
+#include "sha512_host.h"
 
 #include <algorithm>
 #include <chrono>
@@ -35,6 +36,25 @@ void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
   }
   bytes.assign(total + BUFFER_SLACK, 0);
   for (int i = 0; i < k; ++i) std::memcpy(bytes.data() + off[i], seqs[i], (size_t)lens[i]);
+  // alphabet: with <= 4 distinct letters (DNA) the fill can use a per-row cost table
+  bool seen[256] = {false};
+  int nletters = 0;
+  uint8_t code_of[256] = {0};
+  for (int i = 0; i < k && nletters <= 4; ++i)
+    for (int32_t c = 0; c < lens[i]; ++c) {
+      const uint8_t ch = (uint8_t)seqs[i][c];
+      if (!seen[ch]) {
+        seen[ch] = true;
+        if (nletters < 4) code_of[ch] = (uint8_t)nletters;
+        if (++nletters > 4) break;
+      }
+    }
+  codes.clear();
+  if (nletters <= 4) {
+    codes.assign(bytes.size(), 0);
+    for (int i = 0; i < k; ++i)
+      for (int32_t c = 0; c < lens[i]; ++c) codes[off[i] + c] = code_of[(uint8_t)seqs[i][c]];
+  }
 }
 
 uint64_t total_cells(const SeqPack &pack, const std::vector<TaskIJ> &tasks) {
@@ -139,9 +159,11 @@ DeviceWorker::~DeviceWorker() {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   release(seq_);
+  release(codes_);
   release(res_pen_);
   release(res_dig_);
   release(err_);
+  if (h_res_) cudaFreeHost(h_res_);
   for (cudaEvent_t e : ev_) cudaEventDestroy(e);
 }
 
@@ -186,6 +208,11 @@ void DeviceWorker::load(const SeqPack &pack) {
   ensure(seq_, pack.bytes.size());
   SEQALK_CUDA(cudaMemcpyAsync(seq_.p, pack.bytes.data(), pack.bytes.size(), cudaMemcpyHostToDevice,
                               slots_[0].stream));
+  if (!pack.codes.empty()) {
+    ensure(codes_, pack.codes.size());
+    SEQALK_CUDA(cudaMemcpyAsync(codes_.p, pack.codes.data(), pack.codes.size(), cudaMemcpyHostToDevice,
+                                slots_[0].stream));
+  }
   SEQALK_CUDA(cudaStreamSynchronize(slots_[0].stream));
 }
 
@@ -203,7 +230,11 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   pgap_ = pgap;
   batches_.clear();
   stats_ = JobStats();
-  constexpr int R = FILL_R;
+  // kernel variant
+  variant_ = FillVariant();
+  if (const char *e = std::getenv("SEQALK_FILL_R")) variant_.R = std::atoi(e) == 16 ? 16 : 8;
+  if (const char *e = std::getenv("SEQALK_FILL_ADD")) variant_.addmode = std::atoi(e) ? 1 : 0;
+  const int R = variant_.R;
   int64_t maxlen = 1;
   Batch cur{0, 0, 0, 0, 0, 0};
   for (size_t t = 0; t < tasks_.size(); ++t) {
@@ -232,15 +263,41 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   // fast path needs non-negative penalties and scores far from int32 overflow
   // (|H'| <= 2*max(pxy,pgap)*(m+n)); anything else takes the exact-select kernel.
   const int64_t pmax = std::max<int64_t>(std::max(pxy, pgap), 1);
-  general_ = pxy < 0 || pgap < 0 || pmax * 4 * maxlen >= (1ll << 29);
+  bool general = pxy < 0 || pgap < 0 || pmax * 4 * maxlen >= (1ll << 29);
   if (const char *e = std::getenv("SEQALK_FORCE_GENERAL"))
-    if (std::atoi(e)) general_ = true;
+    if (std::atoi(e)) general = true;
+  // cost table (PRMT) needs <= 4 letters and both shifted costs in a signed byte
+  bool table = !pack_->codes.empty() && 2 * (int64_t)pgap <= 127 && (int64_t)pxy - 2 * (int64_t)pgap <= 127 &&
+               (int64_t)pxy - 2 * (int64_t)pgap >= -128;
+  if (const char *e = std::getenv("SEQALK_FILL_TAB"))
+    if (!std::atoi(e)) table = false;
+  variant_.mode = general ? MODE_GENERAL : (table ? MODE_TAB : MODE_CMP);
+  // buffer sizes: the largest batch decides, so that run() never reallocates mid-job
+  need_ = Batch{0, 0, 0, 0, 0, 0};
+  for (const Batch &b : batches_) {
+    need_.count = std::max(need_.count, b.count);
+    need_.dir_bytes = std::max(need_.dir_bytes, b.dir_bytes);
+    need_.brow_ints = std::max(need_.brow_ints, b.brow_ints);
+    need_.out_bytes = std::max(need_.out_bytes, b.out_bytes);
+    need_.nstrips = std::max(need_.nstrips, b.nstrips);
+  }
 }
 
 void DeviceWorker::run(int32_t *penalties_dev, uint8_t *digests_dev) {
+  run_impl(penalties_dev, digests_dev, nullptr, nullptr);
+}
+
+void DeviceWorker::run_and_fold(int32_t *penalties_host, char digest_hex_out[129]) {
+  if (!result_slots_.empty()) throw std::runtime_error("run_and_fold needs identity result slots");
+  run_impl(nullptr, nullptr, penalties_host, digest_hex_out);
+}
+
+void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties,
+                            char *fold_hex) {
   SEQALK_CUDA(cudaSetDevice(dev_));
+  const bool streaming = fold_hex != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
-  constexpr int R = FILL_R;
+  const int R = variant_.R;
   const size_t T = tasks_.size();
   if (!penalties_dev) {
     ensure(res_pen_, std::max<size_t>(T, 1) * sizeof(int32_t));
@@ -250,34 +307,62 @@ void DeviceWorker::run(int32_t *penalties_dev, uint8_t *digests_dev) {
     ensure(res_dig_, std::max<size_t>(T, 1) * 64);
     digests_dev = static_cast<uint8_t *>(res_dig_.p);
   }
-  // events: 4 per batch (fill start/end, traceback end, digest end)
-  while (ev_.size() < 4 * batches_.size()) {
+  int32_t *h_pen = nullptr;
+  uint8_t *h_dig = nullptr;
+  size_t next_fold = 0, hex_len = 0;
+  if (streaming) {
+    const size_t want = std::max<size_t>(T, 1) * 68;
+    if (want > h_res_cap_) {
+      if (h_res_) SEQALK_CUDA(cudaFreeHost(h_res_));
+      h_res_ = nullptr;
+      SEQALK_CUDA(cudaMallocHost(&h_res_, want));
+      h_res_cap_ = want;
+    }
+    h_pen = static_cast<int32_t *>(h_res_);
+    h_dig = static_cast<uint8_t *>(h_res_) + std::max<size_t>(T, 1) * 4;
+    fold_hex[0] = 0;
+  }
+  auto fold_ready = [&](bool wait) {
+    while (next_fold < batches_.size()) {
+      cudaEvent_t done = ev_[5 * next_fold + 4];
+      if (wait) {
+        SEQALK_CUDA(cudaEventSynchronize(done));
+      } else {
+        cudaError_t q = cudaEventQuery(done);
+        if (q == cudaErrorNotReady) break;
+        SEQALK_CUDA(q);
+      }
+      const Batch &FB = batches_[next_fold];
+      fold_chain(h_dig + 64 * FB.first, FB.count, fold_hex, &hex_len);
+      std::memcpy(fold_penalties + FB.first, h_pen + FB.first, FB.count * sizeof(int32_t));
+      ++next_fold;
+    }
+  };
+  // events: 5 per batch (fill start/end, traceback end, digest end, results on host)
+  while (ev_.size() < 5 * batches_.size()) {
     cudaEvent_t e;
     SEQALK_CUDA(cudaEventCreate(&e));
     ev_.push_back(e);
   }
-  SEQALK_CUDA(cudaMemsetAsync(err_.p, 0, sizeof(uint32_t), slots_[0].stream));
-  SEQALK_CUDA(cudaStreamSynchronize(slots_[0].stream));
 
   for (size_t b = 0; b < batches_.size(); ++b) {
     const Batch &B = batches_[b];
     Slot &S = slots_[b % nslots_];
-    // ---- size device buffers
-    ensure(S.pairs, B.count * sizeof(PairDesc));
-    ensure(S.tasks, (size_t)B.nstrips * sizeof(StripTask));
-    ensure(S.slots, B.count * sizeof(uint32_t));
-    ensure(S.progress, (size_t)B.nstrips * sizeof(uint32_t));
-    ensure(S.brow, B.brow_ints * sizeof(int32_t));
-    ensure(S.dirs, B.dir_bytes);
-    ensure(S.out, B.out_bytes + BUFFER_SLACK);
-    ensure(S.align, B.count * sizeof(PairAlign));
-    ensure(S.pen, B.count * sizeof(int32_t));
-    ensure(S.cost, B.count * sizeof(int32_t));
+    // ---- size device buffers (for the largest batch of the job: at most one allocation)
+    ensure(S.pairs, need_.count * sizeof(PairDesc));
+    ensure(S.tasks, (size_t)need_.nstrips * sizeof(StripTask));
+    ensure(S.slots, need_.count * sizeof(uint32_t));
+    ensure(S.progress, (size_t)need_.nstrips * sizeof(uint32_t));
+    ensure(S.brow, need_.brow_ints * sizeof(int32_t));
+    ensure(S.dirs, need_.dir_bytes);
+    ensure(S.out, need_.out_bytes + BUFFER_SLACK);
+    ensure(S.align, need_.count * sizeof(PairAlign));
+    ensure(S.cost, need_.count * sizeof(int32_t));
     ensure(S.counter, sizeof(uint32_t));
     // ---- build descriptors in pinned staging
-    const size_t pairs_bytes = round_up(B.count * sizeof(PairDesc), 256);
-    const size_t tasks_bytes = round_up((size_t)B.nstrips * sizeof(StripTask), 256);
-    const size_t slots_bytes = round_up(B.count * sizeof(uint32_t), 256);
+    const size_t pairs_bytes = round_up(need_.count * sizeof(PairDesc), 256);
+    const size_t tasks_bytes = round_up((size_t)need_.nstrips * sizeof(StripTask), 256);
+    const size_t slots_bytes = round_up(need_.count * sizeof(uint32_t), 256);
     ensure_stage(S, pairs_bytes + tasks_bytes + slots_bytes);
     if (S.staged_pending) {
       SEQALK_CUDA(cudaEventSynchronize(S.staged));
@@ -331,6 +416,8 @@ void DeviceWorker::run(int32_t *penalties_dev, uint8_t *digests_dev) {
 
     FillArgs fa;
     fa.seq = static_cast<const uint8_t *>(seq_.p);
+    fa.codes = static_cast<const uint8_t *>(codes_.p);
+    fa.one = 1;
     fa.pairs = static_cast<const PairDesc *>(S.pairs.p);
     fa.tasks = static_cast<const StripTask *>(S.tasks.p);
     fa.ntasks = B.nstrips;
@@ -338,12 +425,11 @@ void DeviceWorker::run(int32_t *penalties_dev, uint8_t *digests_dev) {
     fa.progress = static_cast<uint32_t *>(S.progress.p);
     fa.brow = static_cast<int32_t *>(S.brow.p);
     fa.dirs = static_cast<uint8_t *>(S.dirs.p);
-    fa.penalties = static_cast<int32_t *>(S.pen.p);
     fa.pxy = pxy_;
     fa.pgap = pgap_;
-    SEQALK_CUDA(cudaEventRecord(ev_[4 * b + 0], st));
-    SEQALK_CUDA(launch_fill(fa, general_, sm_count_, st));
-    SEQALK_CUDA(cudaEventRecord(ev_[4 * b + 1], st));
+    SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 0], st));
+    SEQALK_CUDA(launch_fill(fa, variant_, sm_count_, st));
+    SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 1], st));
 
     TracebackArgs ta;
     ta.seq = fa.seq;
@@ -355,40 +441,44 @@ void DeviceWorker::run(int32_t *penalties_dev, uint8_t *digests_dev) {
     ta.path_cost = static_cast<int32_t *>(S.cost.p);
     ta.pxy = pxy_;
     ta.pgap = pgap_;
+    ta.R = R;
     SEQALK_CUDA(launch_traceback(ta, st));
-    SEQALK_CUDA(cudaEventRecord(ev_[4 * b + 2], st));
+    SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 2], st));
 
     DigestArgs da;
     da.pairs = fa.pairs;
     da.npairs = (uint32_t)B.count;
     da.out = ta.out;
     da.align = ta.align;
-    da.penalties = fa.penalties;
-    da.path_cost = ta.path_cost;
+    da.penalties = ta.path_cost;
     da.result_slot = static_cast<const uint32_t *>(S.slots.p);
     da.digests = digests_dev;
     da.penalties_out = penalties_dev;
-    da.error_flag = static_cast<uint32_t *>(err_.p);
     SEQALK_CUDA(launch_digest(da, st));
-    SEQALK_CUDA(cudaEventRecord(ev_[4 * b + 3], st));
+    SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 3], st));
+    if (streaming) {
+      SEQALK_CUDA(cudaMemcpyAsync(h_pen + B.first, penalties_dev + B.first, B.count * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, st));
+      SEQALK_CUDA(cudaMemcpyAsync(h_dig + 64 * B.first, digests_dev + 64 * B.first, B.count * 64,
+                                  cudaMemcpyDeviceToHost, st));
+      SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 4], st));
+      fold_ready(false);  // fold whatever has landed while the GPU works on later batches
+    }
     stats_.fill_launches++;
     stats_.traceback_launches++;
     stats_.digest_launches++;
   }
+  if (streaming) fold_ready(true);
   for (Slot &S : slots_) SEQALK_CUDA(cudaStreamSynchronize(S.stream));
   for (Slot &S : slots_) S.staged_pending = false;
-  uint32_t err = 0;
-  SEQALK_CUDA(cudaMemcpy(&err, err_.p, sizeof err, cudaMemcpyDeviceToHost));
-  if (err)
-    throw std::runtime_error("internal check failed: traceback path cost != dp[m][n] for at least one pair");
   stats_.fill_ms = stats_.traceback_ms = stats_.digest_ms = 0;
   for (size_t b = 0; b < batches_.size(); ++b) {
     float ms = 0;
-    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[4 * b + 0], ev_[4 * b + 1]));
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[5 * b + 0], ev_[5 * b + 1]));
     stats_.fill_ms += ms;
-    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[4 * b + 1], ev_[4 * b + 2]));
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[5 * b + 1], ev_[5 * b + 2]));
     stats_.traceback_ms += ms;
-    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[4 * b + 2], ev_[4 * b + 3]));
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[5 * b + 2], ev_[5 * b + 3]));
     stats_.digest_ms += ms;
   }
   stats_.wall_ms =

@@ -20,6 +20,7 @@ struct SeqPack {
   std::vector<uint8_t> bytes;
   std::vector<uint32_t> off;
   std::vector<int32_t> len;
+  std::vector<uint8_t> codes;  // same layout as bytes with letters remapped to 0..3; empty if > 4 letters
   int k = 0;
   void build(const char *const *seqs, const int32_t *lens, int k);
 };
@@ -55,6 +56,11 @@ class DeviceWorker {
   // both may be null (-> worker-owned device arrays, read back with fetch()) or point
   // into another GPU's memory when peer access is enabled (fused gather over NVLink).
   void run(int32_t *penalties_dev = nullptr, uint8_t *digests_dev = nullptr);
+  // Single-GPU end-to-end path: runs every batch with worker-owned result arrays, copies each
+  // batch's results to the host as soon as its digest kernel is done and folds the hash chain
+  // (submit/xuliny-seqalkway.cpp:334-337) in task order while later batches are still on the
+  // GPU.  Requires identity result slots.  penalties_host[T], digest_hex_out[129].
+  void run_and_fold(int32_t *penalties_host, char digest_hex_out[129]);
   // D2H of worker-owned results.
   void fetch(int32_t *penalties_host, uint8_t *digests_host);
   // Alignment strings of the LAST batch's pair `index_in_job` (only valid when the job is
@@ -92,15 +98,19 @@ class DeviceWorker {
   size_t dir_budget_ = 0;
   int nslots_ = 2;
   std::vector<Slot> slots_;
-  DevBuf seq_;
+  DevBuf seq_, codes_;
   const SeqPack *pack_ = nullptr;
   SeqPack pack_copy_;
   std::vector<TaskIJ> tasks_;
   std::vector<uint32_t> result_slots_;
   std::vector<Batch> batches_;
   int pxy_ = 0, pgap_ = 0;
-  bool general_ = false;
+  FillVariant variant_;
+  Batch need_{0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches
   DevBuf res_pen_, res_dig_, err_;
+  void run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties, char *fold_hex);
+  void *h_res_ = nullptr;  // pinned host mirror of the result arrays: T*4 | T*64
+  size_t h_res_cap_ = 0;
   std::vector<cudaEvent_t> ev_;
   JobStats stats_;
 };

@@ -23,8 +23,8 @@
 //         H'[i][j] = match ? H'[i-1][j-1] - 2*pgap
 //                          : min(H'[i-1][j-1] + pxy - 2*pgap, H'[i-1][j], H'[i][j-1])
 //     (comparisons are shift-invariant, so ties break exactly as in the reference);
-//   * per cell a 2-bit code is emitted: bit0 = "not diagonal", bit1 = "left strictly
-//     better than up".  The traceback reads DIAG if !bit0, else LEFT if bit1, else UP —
+//   * per cell a 2-bit code is emitted: bit1 = "not diagonal", bit0 = "left strictly
+//     better than up".  The traceback reads DIAG if !bit1, else LEFT if bit0, else UP —
 //     the reference's priority order (match, mismatch-diag, up, left; :502-531).
 //     128 bits per lane are accumulated in registers and written with one 16 B store;
 //     a warp's store is one contiguous 512 B segment (strip-major, step-skewed layout).
@@ -43,11 +43,29 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// a + b, optionally forced onto the FMA pipe as a*one + b (one == 1 at run time, unknown
+// to ptxas) so that the ALU pipe is left to VIMNMX3 / SHF / ISETP / PRMT.
+template <int ADDMODE>
+__device__ __forceinline__ int add_i(int a, int b, int one) {
+  if (ADDMODE == 0) return a + b;
+  int r;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+  return r;
+}
+template <int ADDMODE>
+__device__ __forceinline__ int sub_i(int a, int b, int minus_one) {  // a - b
+  if (ADDMODE == 0) return a - b;
+  int r;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(minus_one), "r"(a));
+  return r;
+}
+
 // One lane's R x 4 block.  h[r] = H' of row r at the previous column; dg = H' of the row
 // above the block at the previous column; up_in[c] = H' of the row above at column c.
 //
-// Per cell, fast path (pxy >= 0, pgap >= 0, scores far from int32 overflow):
-//     t  = diag + B;  if (x == y) t = diag + A        ISETP + 2 adds
+// Per cell, fast modes (pxy >= 0, pgap >= 0, scores far from int32 overflow):
+//     t  = diag + cost(x, y)                           MODE_CMP: ISETP + add + predicated add
+//                                                      MODE_TAB: PRMT (4-letter table) + add
 //     v  = min3(up, left, t)                           VIMNMX3
 //     d1 = v - t      (< 0  <=>  diagonal not optimal) add
 //     d2 = left - up  (< 0  <=>  left strictly better) add
@@ -55,16 +73,21 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 // On a match the reference takes the diagonal unconditionally (:478-479); with
 // non-negative penalties H[i-1][j-1] <= min(H[i-1][j], H[i][j-1]) + pgap, so the
 // plain minimum selects the same value and sign(d1) = 0 (DIAG) — identical output.
-// GENERAL (any integers): explicit select on match, compares instead of sign tricks.
-template <int R, bool GENERAL, bool CAPTURE>
+// MODE_GENERAL (any integers): explicit select on match, compares instead of sign tricks.
+//
+// xc[r]: MODE_TAB: 4 signed bytes, byte q = cost of row r's character against letter q;
+//        otherwise the raw character code (0x100+r for rows past m: never matches).
+template <int R, int MODE, int ADDMODE>
 __device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)[R], const int (&up_in)[4],
-                                           unsigned yword, int A, int B, int (&outv)[4],
-                                           unsigned (&bits)[R / 4], int cn, int rm, int &captured) {
+                                           unsigned yword, int A, int B, int one, int minus_one,
+                                           int (&outv)[4], unsigned (&bits)[R / 4]) {
 #pragma unroll
   for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int yc = (int)((yword >> (8 * c)) & 0xffu);
+    unsigned sel = 0;
+    if (MODE == MODE_TAB) sel = (unsigned)yc * 0x1111u + 0x8880u;  // byte yc, sign-replicated
     int diag = dg;
     int up = up_in[c];
     dg = up;
@@ -73,17 +96,7 @@ __device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)
       const int w = (c * R + r) / CELLS_PER_WORD;  // cells are shifted in, first cell ends up highest
       const int left = h[r];
       int v;
-      if (!GENERAL) {
-        int t = diag + B;
-        asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p add.s32 %0, %3, %4;}"
-            : "+r"(t)
-            : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A));
-        v = min(min(up, left), t);
-        const int d1 = v - t;
-        const int d2 = left - up;
-        bits[w] = __funnelshift_l((unsigned)d1, bits[w], 1);
-        bits[w] = __funnelshift_l((unsigned)d2, bits[w], 1);
-      } else {
+      if (MODE == MODE_GENERAL) {
         const bool match = (xc[r] == yc);
         const int t = diag + B;
         const int m1 = min(up, left);
@@ -91,36 +104,51 @@ __device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)
         const unsigned nd = ((!match) && (t > m1)) ? 2u : 0u;
         const unsigned lf = (up > left) ? 1u : 0u;
         bits[w] = (bits[w] << 2) | nd | lf;
+      } else {
+        int t;
+        if (MODE == MODE_TAB) {
+          int cost;
+          asm("prmt.b32 %0, %1, %2, %3;" : "=r"(cost) : "r"(xc[r]), "r"(0), "r"(sel));
+          t = add_i<ADDMODE>(diag, cost, one);
+        } else {
+          t = add_i<ADDMODE>(diag, B, one);
+          if (ADDMODE == 0)
+            asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p add.s32 %0, %3, %4;}"
+                : "+r"(t)
+                : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A));
+          else
+            asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p mad.lo.s32 %0, %3, %5, %4;}"
+                : "+r"(t)
+                : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A), "r"(one));
+        }
+        v = min(min(up, left), t);
+        const int d1 = sub_i<ADDMODE>(v, t, minus_one);
+        const int d2 = sub_i<ADDMODE>(left, up, minus_one);
+        bits[w] = __funnelshift_l((unsigned)d1, bits[w], 1);
+        bits[w] = __funnelshift_l((unsigned)d2, bits[w], 1);
       }
       diag = left;
       up = v;
       h[r] = v;
     }
     outv[c] = up;
-    if (CAPTURE) {
-      // H'[m][n]: row register rm after column cn (later columns of this block are padding)
-      if (c == cn) {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (r == rm) captured = h[r];
-      }
-    }
   }
 }
 
-template <int R, bool GENERAL>
-__device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc &P, const int pair_index,
-                                              const int s, const int lane) {
+template <int R, int MODE, int ADDMODE>
+__device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc &P, const int s, const int lane) {
   constexpr int G = 16 / R;  // macro steps per 16 B direction store
   const unsigned FULL = 0xffffffffu;
   const int m = P.m, n = P.n;
   const int nq = (n + 3) >> 2;
   const int ngroups = (nq + 31 + G - 1) / G;
   const int A = -2 * a.pgap, B = a.pxy - 2 * a.pgap;
+  const int one = a.one, minus_one = -a.one;
   const bool first = (s == 0), last = (s == P.nstrips - 1);
 
-  const uint8_t *__restrict__ xs = a.seq + P.x_off;
-  const uint8_t *__restrict__ ys = a.seq + P.y_off;
+  const uint8_t *__restrict__ seqbase = (MODE == MODE_TAB) ? a.codes : a.seq;
+  const uint8_t *__restrict__ xs = seqbase + P.x_off;
+  const unsigned *__restrict__ yw32 = reinterpret_cast<const unsigned *>(seqbase + P.y_off);
   int4 *__restrict__ brow = reinterpret_cast<int4 *>(a.brow + P.brow_off);
   uint4 *__restrict__ dout =
       reinterpret_cast<uint4 *>(a.dirs + P.dir_off + (uint64_t)s * ((uint64_t)ngroups * 512ull)) + lane;
@@ -131,10 +159,18 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   const int row0 = s * (32 * R) + lane * R;
   int xc[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) xc[r] = (row0 + r < m) ? (int)xs[row0 + r] : (0x100 + r);
-
-  // penalty capture: cell (m, n) lives in lane tm, register rm, macro col nq-1, column cn
-  const int tm = ((m - 1) % (32 * R)) / R, rm = (m - 1) % R, cn = (n - 1) & 3;
+  for (int r = 0; r < R; ++r) {
+    const bool inside = row0 + r < m;
+    const int ch = inside ? (int)xs[row0 + r] : 0;
+    if (MODE == MODE_TAB) {
+      const unsigned Ab = (unsigned)A & 0xffu, Bb = (unsigned)B & 0xffu;
+      unsigned tab = Bb * 0x01010101u;
+      if (inside) tab ^= (Ab ^ Bb) << (8 * (ch & 3));
+      xc[r] = (int)tab;
+    } else {
+      xc[r] = inside ? ch : (0x100 + r);
+    }
+  }
 
   int h[R];
 #pragma unroll
@@ -142,49 +178,46 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   int dg = 0;
   int outv[4] = {0, 0, 0, 0};
   unsigned yw = 0;
-
-  // lane 0's software pipeline: boundary values + y words of the NEXT group
-  int4 top_next[G];
-  unsigned y_next[G];
   int avail = first ? nq : 0;  // macro cols of the predecessor's bottom row known to be published
 
-  auto fetch_group = [&](int g, int4(&top)[G], unsigned(&yy)[G]) {
-    // make sure the predecessor strip has published macro cols [g*G, g*G+G)
+  // lane 0's look-ahead: boundary values + y words of the next group.  They are loaded
+  // right after the current group's last use of these registers, one macro step (hundreds
+  // of issue slots) before they are needed: no second buffer, no register moves.
+  int4 top[G];
+  unsigned ynext[G];
+#pragma unroll
+  for (int u = 0; u < G; ++u) {
+    top[u] = make_int4(0, 0, 0, 0);
+    ynext[u] = 0u;
+  }
+  auto fetch_group = [&](int g) {
     const int need = min(nq, g * G + G);
-    if (avail < need) {
+    if (avail < need) {  // predecessor strip still in flight: wait for its next publication
+      unsigned ns = 32;
       for (;;) {
         unsigned v = 0;
         if (lane == 0) v = ld_acquire_u32(prev_progress);
         v = __shfl_sync(FULL, v, 0);
         avail = (int)v;
         if (avail >= need) break;
-        __nanosleep(64);
+        __nanosleep(ns);
+        if (ns < 2048) ns *= 2;
       }
     }
+    if (lane == 0) {
 #pragma unroll
-    for (int u = 0; u < G; ++u) {
-      const int qc = g * G + u;
-      top[u] = make_int4(0, 0, 0, 0);
-      yy[u] = 0u;
-      if (lane == 0 && qc < nq) {
-        yy[u] = __ldg(reinterpret_cast<const unsigned *>(ys) + qc);
-        if (!first) top[u] = __ldcg(brow + qc);
+      for (int u = 0; u < G; ++u) {
+        const int qc = g * G + u;
+        if (qc < nq) {
+          ynext[u] = __ldg(yw32 + qc);
+          if (!first) top[u] = __ldcg(brow + qc);
+        }
       }
     }
   };
-
-  fetch_group(0, top_next, y_next);
+  fetch_group(0);
 
   for (int g = 0; g < ngroups; ++g) {
-    int4 top_cur[G];
-    unsigned y_cur[G];
-#pragma unroll
-    for (int u = 0; u < G; ++u) {
-      top_cur[u] = top_next[u];
-      y_cur[u] = y_next[u];
-    }
-    if ((g + 1) * G < nq) fetch_group(g + 1, top_next, y_next);
-
     unsigned pk[4];
 #pragma unroll
     for (int u = 0; u < G; ++u) {
@@ -196,25 +229,20 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
       up_in[3] = __shfl_up_sync(FULL, outv[3], 1);
       unsigned ny = __shfl_up_sync(FULL, yw, 1);
       if (lane == 0) {
-        up_in[0] = top_cur[u].x;
-        up_in[1] = top_cur[u].y;
-        up_in[2] = top_cur[u].z;
-        up_in[3] = top_cur[u].w;
-        ny = y_cur[u];
+        up_in[0] = top[u].x;
+        up_in[1] = top[u].y;
+        up_in[2] = top[u].z;
+        up_in[3] = top[u].w;
+        ny = ynext[u];
       }
+      if (u == G - 1 && (g + 1) * G < nq) fetch_group(g + 1);
       const int qc = q - lane;  // this lane's macro column
       unsigned bits[R / 4];
 #pragma unroll
       for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
       if (qc >= 0 && qc < nq) {
         yw = ny;
-        int cap = 0;
-        if (last && q - tm == nq - 1) {  // warp-uniform, once per pair
-          macro_step<R, GENERAL, true>(h, dg, xc, up_in, yw, A, B, outv, bits, cn, rm, cap);
-          if (lane == tm) a.penalties[pair_index] = cap + (m + n) * a.pgap;
-        } else {
-          macro_step<R, GENERAL, false>(h, dg, xc, up_in, yw, A, B, outv, bits, cn, rm, cap);
-        }
+        macro_step<R, MODE, ADDMODE>(h, dg, xc, up_in, yw, A, B, one, minus_one, outv, bits);
         if (lane == 31 && !last) brow[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
       }
 #pragma unroll
@@ -225,16 +253,17 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
     // publish progress of the bottom row (lane 31 trails by 31 macro steps)
     if (!last) {
       const int done = min(nq, (g + 1) * G - 31);
-      const int prev_done = min(nq, g * G - 31);
-      if (done > 0 && ((done / PUBLISH_EVERY) != (max(prev_done, 0) / PUBLISH_EVERY) || done == nq) &&
-          done != prev_done) {
-        if (lane == 31) st_release_u32(my_progress, (unsigned)done);
+      if (done > 0) {
+        const int prev_done = max(0, min(nq, g * G - 31));
+        if (done != prev_done && (done == nq || (done / PUBLISH_EVERY) != (prev_done / PUBLISH_EVERY))) {
+          if (lane == 31) st_release_u32(my_progress, (unsigned)done);
+        }
       }
     }
   }
 }
 
-template <int R, bool GENERAL>
+template <int R, int MODE, int ADDMODE>
 __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillArgs a) {
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -244,31 +273,44 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillArgs a) {
     if (t >= a.ntasks) break;
     const StripTask task = a.tasks[t];
     const PairDesc P = a.pairs[task.pair];
-    process_strip<R, GENERAL>(a, P, (int)task.pair, (int)task.strip, lane);
+    process_strip<R, MODE, ADDMODE>(a, P, (int)task.strip, lane);
   }
 }
 
-int fill_blocks_per_sm(bool general) {
+typedef void (*FillKernelPtr)(const FillArgs);
+
+static FillKernelPtr pick_kernel(const FillVariant &v) {
+#define SEQALK_PICK(RR)                                                                     \
+  if (v.R == RR) {                                                                          \
+    if (v.mode == MODE_GENERAL) return fill_kernel<RR, MODE_GENERAL, 0>;                    \
+    if (v.mode == MODE_CMP) return v.addmode ? fill_kernel<RR, MODE_CMP, 1> : fill_kernel<RR, MODE_CMP, 0>; \
+    if (v.mode == MODE_TAB) return v.addmode ? fill_kernel<RR, MODE_TAB, 1> : fill_kernel<RR, MODE_TAB, 0>; \
+  }
+  SEQALK_PICK(8)
+  SEQALK_PICK(16)
+#undef SEQALK_PICK
+  return nullptr;
+}
+
+int fill_blocks_per_sm(const FillVariant &v) {
+  FillKernelPtr k = pick_kernel(v);
+  if (!k) return 0;
   int nb = 0;
-  if (general)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_kernel<FILL_R, true>, FILL_THREADS, 0);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_kernel<FILL_R, false>, FILL_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, FILL_THREADS, 0);
   return nb;
 }
 
-cudaError_t launch_fill(const FillArgs &args, bool general, int sm_count, cudaStream_t stream) {
+cudaError_t launch_fill(const FillArgs &args, const FillVariant &v, int sm_count, cudaStream_t stream) {
   if (args.ntasks == 0) return cudaSuccess;
-  int nb = fill_blocks_per_sm(general);
+  FillKernelPtr k = pick_kernel(v);
+  if (!k) return cudaErrorInvalidValue;
+  int nb = fill_blocks_per_sm(v);
   if (nb < 1) return cudaErrorLaunchOutOfResources;
   // persistent grid: every SM full, but no more warps than strips
   long long want = ((long long)args.ntasks + (FILL_THREADS / 32) - 1) / (FILL_THREADS / 32);
   long long grid = (long long)sm_count * nb;
   if (grid > want) grid = want;
-  if (general)
-    fill_kernel<FILL_R, true><<<(unsigned)grid, FILL_THREADS, 0, stream>>>(args);
-  else
-    fill_kernel<FILL_R, false><<<(unsigned)grid, FILL_THREADS, 0, stream>>>(args);
+  k<<<(unsigned)grid, FILL_THREADS, 0, stream>>>(args);
   return cudaGetLastError();
 }
 

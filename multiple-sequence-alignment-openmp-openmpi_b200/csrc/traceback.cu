@@ -12,9 +12,9 @@
 // offset m+n; `start` marks their first byte.
 //
 // One thread per pair: the walk is a dependent chain of <= m+n steps; pairs of a batch
-// run in parallel.  The thread caches the last 32-bit direction word (16 cells = a lane's
-// 8 rows x 2 columns for R = 8), and emits output through 8-byte registers so that the
-// stores are 64-bit, not per character.
+// run in parallel.  The thread caches the last 16 B of directions (64 cells = one lane's
+// R rows x 64/R columns) and emits output through 8-byte registers so that the stores are
+// 64-bit, not per character.
 #include "seqalk_kernels.h"
 
 namespace seqalk {
@@ -46,6 +46,8 @@ struct BackWriter {
 
 template <int R>
 __global__ void __launch_bounds__(TRACEBACK_THREADS) traceback_kernel(const TracebackArgs a) {
+  // 16 B of directions = one lane's R rows x (64/R) columns; the walk usually stays inside
+  // it for several steps, so it is cached in registers.
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.npairs) return;
   const PairDesc P = a.pairs[p];
@@ -58,16 +60,19 @@ __global__ void __launch_bounds__(TRACEBACK_THREADS) traceback_kernel(const Trac
   w2.init(a.out + P.out_off + P.cap, (uint32_t)(m + n));
 
   int i = m, j = n;
-  long long cost = 0;  // path cost, must equal dp[m][n] (checked on the host)
+  long long cost = 0;  // path cost == dp[m][n]: the penalty of this pair
   uint64_t cached_off = ~0ull;
-  uint32_t cached = 0;
+  uint4 cached = make_uint4(0, 0, 0, 0);
   while (i > 0 && j > 0) {
     const DirAddr da = dir_addr(i, j, n, R);
-    if (da.byte_off != cached_off) {
-      cached_off = da.byte_off;
-      cached = __ldcg(reinterpret_cast<const uint32_t *>(dirs + da.byte_off));
+    const uint64_t line = da.byte_off & ~15ull;
+    if (line != cached_off) {
+      cached_off = line;
+      cached = __ldcg(reinterpret_cast<const uint4 *>(dirs + line));
     }
-    const uint32_t code = (cached >> da.shift) & 3u;
+    const uint32_t wsel = (uint32_t)(da.byte_off >> 2) & 3u;
+    const uint32_t word = wsel == 0 ? cached.x : wsel == 1 ? cached.y : wsel == 2 ? cached.z : cached.w;
+    const uint32_t code = (word >> da.shift) & 3u;
     const uint8_t xch = xs[i - 1], ych = ys[j - 1];
     if (!(code & DIR_NOT_DIAG)) {
       w1.put(xch);
@@ -110,7 +115,12 @@ __global__ void __launch_bounds__(TRACEBACK_THREADS) traceback_kernel(const Trac
 cudaError_t launch_traceback(const TracebackArgs &args, cudaStream_t stream) {
   if (args.npairs == 0) return cudaSuccess;
   const unsigned grid = (args.npairs + TRACEBACK_THREADS - 1) / TRACEBACK_THREADS;
-  traceback_kernel<FILL_R><<<grid, TRACEBACK_THREADS, 0, stream>>>(args);
+  if (args.R == 8)
+    traceback_kernel<8><<<grid, TRACEBACK_THREADS, 0, stream>>>(args);
+  else if (args.R == 16)
+    traceback_kernel<16><<<grid, TRACEBACK_THREADS, 0, stream>>>(args);
+  else
+    return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -239,3 +239,35 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     assert pen_t == pen
     p2, _, _ = seqalk.get_minimum_penalty(x[:20000], y[:20000], 3, 2)
     assert p2 == oracle.pair_score(x[:20000], y[:20000], 3, 2)
+
+
+@pytest.mark.parametrize("env", [
+    {"SEQALK_FILL_R": "8", "SEQALK_FILL_TAB": "1", "SEQALK_FILL_ADD": "0"},
+    {"SEQALK_FILL_R": "8", "SEQALK_FILL_TAB": "0", "SEQALK_FILL_ADD": "0"},
+    {"SEQALK_FILL_R": "8", "SEQALK_FILL_TAB": "1", "SEQALK_FILL_ADD": "1"},
+    {"SEQALK_FILL_R": "8", "SEQALK_FILL_TAB": "0", "SEQALK_FILL_ADD": "1"},
+    {"SEQALK_FILL_R": "16", "SEQALK_FILL_TAB": "1", "SEQALK_FILL_ADD": "0"},
+    {"SEQALK_FILL_R": "16", "SEQALK_FILL_TAB": "0", "SEQALK_FILL_ADD": "1"},
+    {"SEQALK_FILL_R": "16", "SEQALK_FORCE_GENERAL": "1"},
+    {"SEQALK_FILL_R": "8", "SEQALK_SLOTS": "1"},
+], ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
+def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatch, env):
+    """Rows per lane (8/16), cost by compare or by 4-letter table, adds on ALU or FMA pipe,
+    general (any-integer) kernel: all must reproduce the oracle bit for bit."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rnd = random.Random(17)
+    lens = [1, 5, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1030, 2049]
+    genes = [bytes(rnd.choice(b"ACGT") for _ in range(L)) for L in lens]
+    with seqalk.Job(genes, 3, 2) as job:  # a fresh worker picks the env up
+        job.run()
+        pen, dig = job.fetch()
+    od, op, oh = oracle.all_pairs(genes, 3, 2, want_pair_hashes=True)
+    assert np.array_equal(pen, op)
+    assert [d.tobytes().hex() for d in dig] == oh
+    genes3 = [bytes(rnd.choice(b"ACG") for _ in range(rnd.randint(1, 700))) for _ in range(5)]
+    with seqalk.Job(genes3, 5, 1) as job:
+        job.run()
+        pen, dig = job.fetch()
+    od, op, oh = oracle.all_pairs(genes3, 5, 1, want_pair_hashes=True)
+    assert np.array_equal(pen, op) and [d.tobytes().hex() for d in dig] == oh
