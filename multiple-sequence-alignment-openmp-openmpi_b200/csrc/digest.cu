@@ -125,7 +125,9 @@ __device__ __forceinline__ uint64_t hex8(uint32_t v) {
   return out;
 }
 
-__global__ void __launch_bounds__(DIGEST_THREADS) digest_kernel(const DigestArgs a) {
+// <= 64 registers so that a CTA fits into the sliver of the register file the persistent
+// fill kernel leaves free (see fill_blocks_per_sm).
+__global__ void __launch_bounds__(DIGEST_THREADS, 16) digest_kernel(const DigestArgs a) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t p = tid >> 1, which = tid & 1;
   const bool valid = p < a.npairs;

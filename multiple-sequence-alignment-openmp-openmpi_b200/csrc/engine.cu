@@ -22,6 +22,7 @@ void throw_cuda(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t EV = 6;  // timing events per batch
 
 void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
   k = k_;
@@ -134,9 +135,14 @@ DeviceWorker::DeviceWorker(int device) : dev_(device) {
   const size_t cap = (size_t)((double)free_b * 0.80 / nslots_);
   if (dir_budget_ > cap) dir_budget_ = cap;
   slots_.resize(nslots_);
+  int prio_lo = 0, prio_hi = 0;
+  SEQALK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  SEQALK_CUDA(cudaStreamCreateWithPriority(&fill_stream_, cudaStreamNonBlocking, prio_lo));
+  SEQALK_CUDA(cudaStreamCreateWithPriority(&post_stream_, cudaStreamNonBlocking, prio_hi));
   for (Slot &s : slots_) {
-    SEQALK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     SEQALK_CUDA(cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
+    SEQALK_CUDA(cudaEventCreateWithFlags(&s.fill_done, cudaEventDisableTiming));
+    SEQALK_CUDA(cudaEventCreateWithFlags(&s.post_done, cudaEventDisableTiming));
   }
   ensure(err_, sizeof(uint32_t));
 }
@@ -156,8 +162,11 @@ DeviceWorker::~DeviceWorker() {
       release(*b);
     if (s.h_stage) cudaFreeHost(s.h_stage);
     if (s.staged) cudaEventDestroy(s.staged);
-    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.fill_done) cudaEventDestroy(s.fill_done);
+    if (s.post_done) cudaEventDestroy(s.post_done);
   }
+  if (fill_stream_) cudaStreamDestroy(fill_stream_);
+  if (post_stream_) cudaStreamDestroy(post_stream_);
   release(seq_);
   release(codes_);
   release(res_pen_);
@@ -207,13 +216,13 @@ void DeviceWorker::load(const SeqPack &pack) {
   pack_ = &pack_copy_;
   ensure(seq_, pack.bytes.size());
   SEQALK_CUDA(cudaMemcpyAsync(seq_.p, pack.bytes.data(), pack.bytes.size(), cudaMemcpyHostToDevice,
-                              slots_[0].stream));
+                              fill_stream_));
   if (!pack.codes.empty()) {
     ensure(codes_, pack.codes.size());
     SEQALK_CUDA(cudaMemcpyAsync(codes_.p, pack.codes.data(), pack.codes.size(), cudaMemcpyHostToDevice,
-                                slots_[0].stream));
+                                fill_stream_));
   }
-  SEQALK_CUDA(cudaStreamSynchronize(slots_[0].stream));
+  SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
 }
 
 void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
@@ -232,7 +241,8 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   stats_ = JobStats();
   // kernel variant
   variant_ = FillVariant();
-  if (const char *e = std::getenv("SEQALK_FILL_R")) variant_.R = std::atoi(e) == 16 ? 16 : 8;
+  variant_.R = 16;  // measured best on B200 (profiles/): 16 rows per lane, cost table when possible
+  if (const char *e = std::getenv("SEQALK_FILL_R")) variant_.R = std::atoi(e) == 8 ? 8 : 16;
   if (const char *e = std::getenv("SEQALK_FILL_ADD")) variant_.addmode = std::atoi(e) ? 1 : 0;
   const int R = variant_.R;
   int64_t maxlen = 1;
@@ -324,7 +334,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   }
   auto fold_ready = [&](bool wait) {
     while (next_fold < batches_.size()) {
-      cudaEvent_t done = ev_[5 * next_fold + 4];
+      cudaEvent_t done = ev_[EV * next_fold + 5];
       if (wait) {
         SEQALK_CUDA(cudaEventSynchronize(done));
       } else {
@@ -338,8 +348,9 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       ++next_fold;
     }
   };
-  // events: 5 per batch (fill start/end, traceback end, digest end, results on host)
-  while (ev_.size() < 5 * batches_.size()) {
+  // events per batch: fill start/end (fill stream); traceback start/end, digest end,
+  // results on host (post stream)
+  while (ev_.size() < EV * batches_.size()) {
     cudaEvent_t e;
     SEQALK_CUDA(cudaEventCreate(&e));
     ev_.push_back(e);
@@ -404,8 +415,12 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
           if (s < hp[p].nstrips) ht[w++] = StripTask{(uint32_t)p, (uint32_t)s};
     }
     S.last_pairs.assign(hp, hp + B.count);
-    // ---- enqueue
-    cudaStream_t st = S.stream;
+    // ---- enqueue: fill stream
+    cudaStream_t st = fill_stream_;
+    if (S.post_pending) {  // the slot's buffers are free once its previous batch is post-processed
+      SEQALK_CUDA(cudaStreamWaitEvent(st, S.post_done, 0));
+      S.post_pending = false;
+    }
     SEQALK_CUDA(cudaMemcpyAsync(S.pairs.p, hp, B.count * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
     SEQALK_CUDA(cudaMemcpyAsync(S.tasks.p, ht, (size_t)B.nstrips * sizeof(StripTask), cudaMemcpyHostToDevice, st));
     SEQALK_CUDA(cudaMemcpyAsync(S.slots.p, hs, B.count * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -427,9 +442,14 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.dirs = static_cast<uint8_t *>(S.dirs.p);
     fa.pxy = pxy_;
     fa.pgap = pgap_;
-    SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 0], st));
+    SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 0], st));
     SEQALK_CUDA(launch_fill(fa, variant_, sm_count_, st));
-    SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 1], st));
+    SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 1], st));
+    SEQALK_CUDA(cudaEventRecord(S.fill_done, st));
+    // ---- enqueue: post stream (high priority; runs under the next batch's fill)
+    st = post_stream_;
+    SEQALK_CUDA(cudaStreamWaitEvent(st, S.fill_done, 0));
+    SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 2], st));
 
     TracebackArgs ta;
     ta.seq = fa.seq;
@@ -443,7 +463,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.pgap = pgap_;
     ta.R = R;
     SEQALK_CUDA(launch_traceback(ta, st));
-    SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 2], st));
+    SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));
 
     DigestArgs da;
     da.pairs = fa.pairs;
@@ -455,30 +475,33 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     da.digests = digests_dev;
     da.penalties_out = penalties_dev;
     SEQALK_CUDA(launch_digest(da, st));
-    SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 3], st));
+    SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 4], st));
     if (streaming) {
       SEQALK_CUDA(cudaMemcpyAsync(h_pen + B.first, penalties_dev + B.first, B.count * sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, st));
       SEQALK_CUDA(cudaMemcpyAsync(h_dig + 64 * B.first, digests_dev + 64 * B.first, B.count * 64,
                                   cudaMemcpyDeviceToHost, st));
-      SEQALK_CUDA(cudaEventRecord(ev_[5 * b + 4], st));
-      fold_ready(false);  // fold whatever has landed while the GPU works on later batches
+      SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 5], st));
     }
+    SEQALK_CUDA(cudaEventRecord(S.post_done, st));
+    S.post_pending = true;
+    if (streaming) fold_ready(false);  // fold what has landed while the GPU works on later batches
     stats_.fill_launches++;
     stats_.traceback_launches++;
     stats_.digest_launches++;
   }
   if (streaming) fold_ready(true);
-  for (Slot &S : slots_) SEQALK_CUDA(cudaStreamSynchronize(S.stream));
-  for (Slot &S : slots_) S.staged_pending = false;
+  SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
+  SEQALK_CUDA(cudaStreamSynchronize(post_stream_));
+  for (Slot &S : slots_) S.staged_pending = S.post_pending = false;
   stats_.fill_ms = stats_.traceback_ms = stats_.digest_ms = 0;
   for (size_t b = 0; b < batches_.size(); ++b) {
     float ms = 0;
-    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[5 * b + 0], ev_[5 * b + 1]));
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[EV * b + 0], ev_[EV * b + 1]));
     stats_.fill_ms += ms;
-    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[5 * b + 1], ev_[5 * b + 2]));
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[EV * b + 2], ev_[EV * b + 3]));
     stats_.traceback_ms += ms;
-    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[5 * b + 2], ev_[5 * b + 3]));
+    SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[EV * b + 3], ev_[EV * b + 4]));
     stats_.digest_ms += ms;
   }
   stats_.wall_ms =

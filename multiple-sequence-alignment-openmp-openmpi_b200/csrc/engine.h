@@ -3,8 +3,10 @@
 // Plays the role of the reference's worker loop (recv Triple -> do_task -> send Packet,
 // submit/xuliny-seqalkway.cpp:342-357, 399-411) for one device: takes a list of (i, j)
 // tasks, cuts it into batches that fit the HBM budget for packed directions, and for each
-// batch runs  fill -> traceback -> digest  on one of NSLOT streams so that the latency-bound
-// traceback of batch b overlaps the fill of batch b+1.
+// batch runs  fill  on the fill stream and  traceback -> digest (-> D2H)  on a second,
+// high-priority stream, double-buffered over NSLOT buffer sets, so that the latency-bound
+// traceback of batch b runs under the fill of batch b+1 (the fill leaves a sliver of every
+// SM's registers free for it).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -81,7 +83,9 @@ class DeviceWorker {
     size_t cap = 0;
   };
   struct Slot {
-    cudaStream_t stream = nullptr;
+    cudaEvent_t fill_done = nullptr;   // fill of the batch using this slot finished
+    cudaEvent_t post_done = nullptr;   // traceback + digest (+ D2H) of that batch finished
+    bool post_pending = false;
     DevBuf pairs, tasks, slots, progress, brow, dirs, out, align, pen, cost, counter;
     void *h_stage = nullptr;  // pinned staging: pairs | tasks | slots
     size_t h_cap = 0;
@@ -98,6 +102,7 @@ class DeviceWorker {
   size_t dir_budget_ = 0;
   int nslots_ = 2;
   std::vector<Slot> slots_;
+  cudaStream_t fill_stream_ = nullptr, post_stream_ = nullptr;
   DevBuf seq_, codes_;
   const SeqPack *pack_ = nullptr;
   SeqPack pack_copy_;

@@ -28,6 +28,8 @@
 //     the reference's priority order (match, mismatch-diag, up, left; :502-531).
 //     128 bits per lane are accumulated in registers and written with one 16 B store;
 //     a warp's store is one contiguous 512 B segment (strip-major, step-skewed layout).
+#include <cstdlib>
+
 #include "seqalk_kernels.h"
 
 namespace seqalk {
@@ -37,6 +39,11 @@ constexpr int FILL_THREADS = 128;
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
@@ -193,16 +200,21 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   auto fetch_group = [&](int g) {
     const int need = min(nq, g * G + G);
     if (avail < need) {  // predecessor strip still in flight: wait for its next publication
+      // Poll with relaxed loads (an acquire load invalidates the SM's whole L1 — CCTL.IVALL —
+      // which would evict the co-resident traceback / digest kernels' lines on every poll);
+      // one acquire load once the value is there orders the boundary reads after it.
       unsigned ns = 32;
       for (;;) {
         unsigned v = 0;
-        if (lane == 0) v = ld_acquire_u32(prev_progress);
+        if (lane == 0) v = ld_relaxed_u32(prev_progress);
         v = __shfl_sync(FULL, v, 0);
-        avail = (int)v;
-        if (avail >= need) break;
+        if ((int)v >= need) break;
         __nanosleep(ns);
-        if (ns < 2048) ns *= 2;
+        if (ns < 4096) ns *= 2;
       }
+      unsigned v = 0;
+      if (lane == 0) v = ld_acquire_u32(prev_progress);
+      avail = (int)__shfl_sync(FULL, v, 0);
     }
     if (lane == 0) {
 #pragma unroll
@@ -292,11 +304,21 @@ static FillKernelPtr pick_kernel(const FillVariant &v) {
   return nullptr;
 }
 
+// Resident fill CTAs per SM.  The fill is a persistent kernel; it must leave room for the
+// small traceback / digest CTAs of the previous batch (<= 64 threads x 64 registers), which
+// run concurrently on the high-priority stream: keep >= 4096 registers of every SM free.
 int fill_blocks_per_sm(const FillVariant &v) {
   FillKernelPtr k = pick_kernel(v);
   if (!k) return 0;
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, FILL_THREADS, 0);
+  cudaFuncAttributes attr;
+  if (cudaFuncGetAttributes(&attr, k) == cudaSuccess) {
+    const int regs_alloc = (attr.numRegs + 7) / 8 * 8;
+    int headroom = 4096;
+    if (const char *e = getenv("SEQALK_FILL_HEADROOM_REGS")) headroom = atoi(e);
+    while (nb > 1 && 65536 - nb * FILL_THREADS * regs_alloc < headroom) --nb;
+  }
   return nb;
 }
 

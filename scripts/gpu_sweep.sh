@@ -3,7 +3,7 @@
 WL=${1:-cfg3}
 mkdir -p gpurun_out
 : > gpurun_out/sweep.txt
-for R in 8 16; do for TAB in 1 0; do for ADD in 0 1; do
+for R in ${SWEEP_R:-8 16}; do for TAB in ${SWEEP_TAB:-1 0}; do for ADD in ${SWEEP_ADD:-0 1}; do
   export SEQALK_FILL_R=$R SEQALK_FILL_TAB=$TAB SEQALK_FILL_ADD=$ADD
   python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys,os

@@ -271,3 +271,30 @@ def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatc
         pen, dig = job.fetch()
     od, op, oh = oracle.all_pairs(genes3, 5, 1, want_pair_hashes=True)
     assert np.array_equal(pen, op) and [d.tobytes().hex() for d in dig] == oh
+
+
+def _gpu_count():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def test_two_gpus_in_process_match_one_gpu(seqalk, oracle, workloads):
+    """seqalk_init(2): pairs sharded by cells over two GPUs from one process, results stored
+    by the digest kernel straight into GPU 0's task-ordered arrays (peer stores over NVLink)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    genes = workloads.mixed(16, seed=31, lo=200, hi=3000)
+    od, op, _ = oracle.all_pairs(genes, 3, 2)
+    try:
+        seqalk.init(2)
+        assert seqalk.device_count() == 2
+        d2, p2 = seqalk.get_minimum_penalties(genes, 3, 2)
+        os.environ["SEQALK_P2P"] = "0"   # unfused comparison: per-GPU D2H + host scatter
+        seqalk.init(2)
+        d2b, p2b = seqalk.get_minimum_penalties(genes, 3, 2)
+    finally:
+        os.environ.pop("SEQALK_P2P", None)
+        seqalk.init(1)
+    assert d2 == od and np.array_equal(p2, op)
+    assert d2b == od and np.array_equal(p2b, op)
