@@ -97,6 +97,12 @@ int seqalk_job_create(int32_t device, const char *const *seqs, const int32_t *le
  * DEVICE memory: penalties_dev (int32 per slot) and digests_dev (64 raw bytes per slot); pass
  * NULL for job-owned buffers (read them back with seqalk_job_fetch). */
 int seqalk_job_run(seqalk_job_t *job, void *penalties_dev, void *digests_dev);
+/* Cuts the job into chunks of consecutive result slots: chunk c covers slots
+ * [chunk_ends[c-1], chunk_ends[c]) (chunk_ends[nchunks-1] must equal the task count), so that
+ * a caller can gather / fold chunk c while the GPU works on chunk c+1. */
+int seqalk_job_set_chunks(seqalk_job_t *job, const int64_t *chunk_ends, int32_t nchunks);
+/* Like seqalk_job_run for one chunk; the pointers address the WHOLE job's result arrays. */
+int seqalk_job_run_chunk(seqalk_job_t *job, int32_t chunk, void *penalties_dev, void *digests_dev);
 /* D2H of the job-owned results. */
 int seqalk_job_fetch(seqalk_job_t *job, int32_t *penalties_out, uint8_t *digests_out);
 int seqalk_job_stats(const seqalk_job_t *job, seqalk_stats_t *stats_out);

@@ -72,6 +72,8 @@ C_ABI = [
     ("seqalk_partition_all", _c.c_int, [_I32P, _c.c_int32, _c.c_int64, _c.c_int64, _c.c_int32, _I64P, _I64P]),
     ("seqalk_job_create", _c.c_int, [_c.c_int32, _c.POINTER(_c.c_void_p), _I32P, _c.c_int32, _c.c_int32, _c.c_int32, _I64P, _c.c_int64, _c.POINTER(_c.c_void_p)]),
     ("seqalk_job_run", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    ("seqalk_job_set_chunks", _c.c_int, [_c.c_void_p, _I64P, _c.c_int32]),
+    ("seqalk_job_run_chunk", _c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p]),
     ("seqalk_job_fetch", _c.c_int, [_c.c_void_p, _I32P, _U8P]),
     ("seqalk_job_stats", _c.c_int, [_c.c_void_p, _c.POINTER(_Stats)]),
     ("seqalk_job_destroy", None, [_c.c_void_p]),
@@ -296,6 +298,16 @@ class Job:
     def run(self, penalties_dev: int = 0, digests_dev: int = 0) -> None:
         _check(lib().seqalk_job_run(self._h, ctypes.c_void_p(penalties_dev or None),
                                     ctypes.c_void_p(digests_dev or None)))
+
+    def set_chunks(self, chunk_ends: Sequence[int]) -> None:
+        """Cut the job into chunks of consecutive result slots (cumulative end indices)."""
+        ends = np.ascontiguousarray(np.asarray(chunk_ends, dtype=np.int64))
+        _check(lib().seqalk_job_set_chunks(self._h, ends.ctypes.data_as(_I64P), len(ends)))
+
+    def run_chunk(self, chunk: int, penalties_dev: int = 0, digests_dev: int = 0) -> None:
+        """run() for one chunk; the device pointers address the whole job's result arrays."""
+        _check(lib().seqalk_job_run_chunk(self._h, int(chunk), ctypes.c_void_p(penalties_dev or None),
+                                          ctypes.c_void_p(digests_dev or None)))
 
     def fetch(self) -> Tuple[np.ndarray, np.ndarray]:
         pen = np.zeros(max(self.ntasks, 1), dtype=np.int32)

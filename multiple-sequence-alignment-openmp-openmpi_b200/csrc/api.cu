@@ -187,6 +187,8 @@ void run_tasks(Runtime &r, const SeqPack &pack, const std::vector<TaskIJ> &tasks
 
 struct seqalk_job {
   std::unique_ptr<DeviceWorker> worker;
+  std::vector<TaskIJ> tasks;
+  int pxy = 0, pgap = 0;
 };
 
 extern "C" {
@@ -352,7 +354,37 @@ int seqalk_job_create(int32_t device, const char *const *seqs, const int32_t *le
     job->worker.reset(new DeviceWorker(device));
     job->worker->load(pack);
     job->worker->plan(tasks, pxy, pgap);
+    job->tasks = tasks;
+    job->pxy = pxy;
+    job->pgap = pgap;
     *job_out = job.release();
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_set_chunks(seqalk_job_t *job, const int64_t *chunk_ends, int32_t nchunks) {
+  try {
+    if (!job || !chunk_ends || nchunks < 1) return fail("bad argument");
+    std::vector<size_t> ends(nchunks);
+    for (int c = 0; c < nchunks; ++c) {
+      if (chunk_ends[c] < 0 || (c && chunk_ends[c] < chunk_ends[c - 1])) return fail("chunk ends must increase");
+      ends[c] = (size_t)chunk_ends[c];
+    }
+    if (ends.back() != job->tasks.size()) return fail("last chunk end must equal the number of tasks");
+    job->worker->plan(job->tasks, job->pxy, job->pgap, nullptr, &ends);
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_run_chunk(seqalk_job_t *job, int32_t chunk, void *penalties_dev, void *digests_dev) {
+  try {
+    if (!job || chunk < 0) return fail("bad argument");
+    job->worker->run_chunk((size_t)chunk, static_cast<int32_t *>(penalties_dev),
+                           static_cast<uint8_t *>(digests_dev));
     return 0;
   } catch (const std::exception &e) {
     return fail(e);

@@ -226,7 +226,7 @@ void DeviceWorker::load(const SeqPack &pack) {
 }
 
 void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
-                        const std::vector<uint32_t> *result_slots) {
+                        const std::vector<uint32_t> *result_slots, const std::vector<size_t> *chunk_ends) {
   if (!pack_) throw std::runtime_error("plan() before load()");
   tasks_ = tasks;
   if (result_slots) {
@@ -247,7 +247,20 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   const int R = variant_.R;
   int64_t maxlen = 1;
   Batch cur{0, 0, 0, 0, 0, 0};
+  std::vector<size_t> ends;
+  if (chunk_ends) ends = *chunk_ends;
+  if (ends.empty() || ends.back() != tasks_.size()) ends.push_back(tasks_.size());
+  chunk_batch_.assign(1, 0);
+  size_t next_end = 0;
   for (size_t t = 0; t < tasks_.size(); ++t) {
+    while (next_end < ends.size() && ends[next_end] <= t) {  // chunk boundary: close the batch
+      if (cur.count) {
+        batches_.push_back(cur);
+        cur = Batch{t, 0, 0, 0, 0, 0};
+      }
+      chunk_batch_.push_back(batches_.size());
+      ++next_end;
+    }
     const TaskIJ &tk = tasks_[t];
     if (tk.i < 0 || tk.i >= pack_->k || tk.j < 0 || tk.j >= pack_->k) throw std::runtime_error("task index out of range");
     const int m = pack_->len[tk.i], n = pack_->len[tk.j];
@@ -269,6 +282,10 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     stats_.dir_bytes += db;
   }
   if (cur.count) batches_.push_back(cur);
+  while (next_end < ends.size()) {
+    chunk_batch_.push_back(batches_.size());
+    ++next_end;
+  }
   stats_.batches = (uint32_t)batches_.size();
   // fast path needs non-negative penalties and scores far from int32 overflow
   // (|H'| <= 2*max(pxy,pgap)*(m+n)); anything else takes the exact-select kernel.
@@ -294,16 +311,21 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
 }
 
 void DeviceWorker::run(int32_t *penalties_dev, uint8_t *digests_dev) {
-  run_impl(penalties_dev, digests_dev, nullptr, nullptr);
+  run_impl(penalties_dev, digests_dev, nullptr, nullptr, 0, batches_.size());
+}
+
+void DeviceWorker::run_chunk(size_t c, int32_t *penalties_dev, uint8_t *digests_dev) {
+  if (c + 1 >= chunk_batch_.size()) throw std::runtime_error("chunk index out of range");
+  run_impl(penalties_dev, digests_dev, nullptr, nullptr, chunk_batch_[c], chunk_batch_[c + 1]);
 }
 
 void DeviceWorker::run_and_fold(int32_t *penalties_host, char digest_hex_out[129]) {
   if (!result_slots_.empty()) throw std::runtime_error("run_and_fold needs identity result slots");
-  run_impl(nullptr, nullptr, penalties_host, digest_hex_out);
+  run_impl(nullptr, nullptr, penalties_host, digest_hex_out, 0, batches_.size());
 }
 
 void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties,
-                            char *fold_hex) {
+                            char *fold_hex, size_t batch_begin, size_t batch_end) {
   SEQALK_CUDA(cudaSetDevice(dev_));
   const bool streaming = fold_hex != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
@@ -319,7 +341,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   }
   int32_t *h_pen = nullptr;
   uint8_t *h_dig = nullptr;
-  size_t next_fold = 0, hex_len = 0;
+  size_t next_fold = batch_begin, hex_len = 0;
   if (streaming) {
     const size_t want = std::max<size_t>(T, 1) * 68;
     if (want > h_res_cap_) {
@@ -333,7 +355,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fold_hex[0] = 0;
   }
   auto fold_ready = [&](bool wait) {
-    while (next_fold < batches_.size()) {
+    while (next_fold < batch_end) {
       cudaEvent_t done = ev_[EV * next_fold + 5];
       if (wait) {
         SEQALK_CUDA(cudaEventSynchronize(done));
@@ -356,7 +378,11 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ev_.push_back(e);
   }
 
-  for (size_t b = 0; b < batches_.size(); ++b) {
+  if (batch_begin == 0) {  // timing counters cover one pass over the job's batches
+    stats_.fill_ms = stats_.traceback_ms = stats_.digest_ms = stats_.wall_ms = 0;
+    stats_.fill_launches = stats_.traceback_launches = stats_.digest_launches = 0;
+  }
+  for (size_t b = batch_begin; b < batch_end; ++b) {
     const Batch &B = batches_[b];
     Slot &S = slots_[b % nslots_];
     // ---- size device buffers (for the largest batch of the job: at most one allocation)
@@ -494,8 +520,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
   SEQALK_CUDA(cudaStreamSynchronize(post_stream_));
   for (Slot &S : slots_) S.staged_pending = S.post_pending = false;
-  stats_.fill_ms = stats_.traceback_ms = stats_.digest_ms = 0;
-  for (size_t b = 0; b < batches_.size(); ++b) {
+  for (size_t b = batch_begin; b < batch_end; ++b) {
     float ms = 0;
     SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[EV * b + 0], ev_[EV * b + 1]));
     stats_.fill_ms += ms;
@@ -504,7 +529,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[EV * b + 3], ev_[EV * b + 4]));
     stats_.digest_ms += ms;
   }
-  stats_.wall_ms =
+  stats_.wall_ms +=
       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 }
 

@@ -52,12 +52,18 @@ class DeviceWorker {
   // H2D of the packed sequences (kept resident until the next load()).
   void load(const SeqPack &pack);
   // Plans batches for `tasks`; result slot of tasks[t] is t unless result_slots is given.
+  // `chunk_ends` (optional, increasing, last == tasks.size()) cuts the job into chunks that
+  // can be run one at a time with run_chunk(); a batch never straddles a chunk end.
   void plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
-            const std::vector<uint32_t> *result_slots = nullptr);
+            const std::vector<uint32_t> *result_slots = nullptr,
+            const std::vector<size_t> *chunk_ends = nullptr);
   // Runs every batch.  Results are written to (penalties_dev[slot], digests_dev[64*slot]);
   // both may be null (-> worker-owned device arrays, read back with fetch()) or point
   // into another GPU's memory when peer access is enabled (fused gather over NVLink).
   void run(int32_t *penalties_dev = nullptr, uint8_t *digests_dev = nullptr);
+  // Runs only chunk c (see plan); the pointers address the WHOLE job's result arrays.
+  void run_chunk(size_t c, int32_t *penalties_dev = nullptr, uint8_t *digests_dev = nullptr);
+  size_t num_chunks() const { return chunk_batch_.empty() ? 0 : chunk_batch_.size() - 1; }
   // Single-GPU end-to-end path: runs every batch with worker-owned result arrays, copies each
   // batch's results to the host as soon as its digest kernel is done and folds the hash chain
   // (submit/xuliny-seqalkway.cpp:334-337) in task order while later batches are still on the
@@ -113,7 +119,9 @@ class DeviceWorker {
   FillVariant variant_;
   Batch need_{0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches
   DevBuf res_pen_, res_dig_, err_;
-  void run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties, char *fold_hex);
+  void run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties, char *fold_hex,
+                size_t batch_begin, size_t batch_end);
+  std::vector<size_t> chunk_batch_;  // chunk c = batches [chunk_batch_[c], chunk_batch_[c+1])
   void *h_res_ = nullptr;  // pinned host mirror of the result arrays: T*4 | T*64
   size_t h_res_cap_ = 0;
   std::vector<cudaEvent_t> ev_;

@@ -53,7 +53,8 @@ class ShardPlan:
 
 
 class GpuShard:
-    """A rank's tasks resident on its GPU: one Job per chunk, results into torch tensors."""
+    """A rank's tasks resident on its GPU: ONE job (one set of device buffers) cut into the
+    plan's chunks; results land in two torch tensors covering all of the rank's tasks."""
 
     def __init__(self, genes: Sequence[bytes], pxy: int, pgap: int, plan: ShardPlan, rank: int, device: int):
         import torch
@@ -61,31 +62,38 @@ class GpuShard:
         self.torch = torch
         self.device = torch.device("cuda", device)
         self.plan, self.rank = plan, rank
-        self.jobs = [Job(genes, pxy, pgap, plan.ids[c][rank], device=device) for c in range(plan.nchunks)]
+        counts = [len(plan.ids[c][rank]) for c in range(plan.nchunks)]
+        self.ends = np.cumsum(counts).astype(np.int64)
+        self.starts = self.ends - np.asarray(counts, dtype=np.int64)
+        ids = plan.rank_ids(rank)
+        self.n = len(ids)
+        self.job = Job(genes, pxy, pgap, ids, device=device) if self.n else None
+        if self.job is not None:
+            self.job.set_chunks(self.ends)
+        self.pen = torch.zeros(max(self.n, 1), dtype=torch.int32, device=self.device)
+        self.dig = torch.zeros((max(self.n, 1), 64), dtype=torch.uint8, device=self.device)
         # gather buffers: [penalty int32 | 64 digest bytes] = 68 bytes per task, padded to the
         # largest shard of the chunk so that one all_gather_into_tensor moves everything
         self.send = [torch.zeros((max(plan.max_count(c), 1), 68), dtype=torch.uint8, device=self.device)
                      for c in range(plan.nchunks)]
-        self.pen = [torch.zeros(max(len(plan.ids[c][rank]), 1), dtype=torch.int32, device=self.device)
-                    for c in range(plan.nchunks)]
-        self.dig = [torch.zeros((max(len(plan.ids[c][rank]), 1), 64), dtype=torch.uint8, device=self.device)
-                    for c in range(plan.nchunks)]
 
     def run_chunk(self, c: int):
         """fill + traceback + digest of this rank's tasks of chunk c; returns the send buffer."""
-        n = len(self.plan.ids[c][self.rank])
+        lo, hi = int(self.starts[c]), int(self.ends[c])
+        n = hi - lo
         if n:
-            self.jobs[c].run(self.pen[c].data_ptr(), self.dig[c].data_ptr())
-            self.send[c][:n, :4] = self.pen[c][:n].view(self.torch.uint8).view(n, 4)
-            self.send[c][:n, 4:] = self.dig[c][:n]
+            self.job.run_chunk(c, self.pen.data_ptr(), self.dig.data_ptr())
+            self.send[c][:n, :4] = self.pen[lo:hi].view(self.torch.uint8).view(n, 4)
+            self.send[c][:n, 4:] = self.dig[lo:hi]
         return self.send[c]
 
     def stats(self):
-        return [j.stats() for j in self.jobs]
+        return [self.job.stats()] if self.job is not None else []
 
     def close(self):
-        for j in self.jobs:
-            j.close()
+        if self.job is not None:
+            self.job.close()
+            self.job = None
 
 
 def _scatter(plan: ShardPlan, c: int, gathered: np.ndarray, penalties: np.ndarray, digests: np.ndarray) -> None:
