@@ -209,7 +209,9 @@ def main():
 
     def step_resident():
         nonlocal result
+        shard.start()
         result = dmod.run_sharded(plan, rank, shard.run_chunk)
+        shard.finish()
 
     for _ in range(args.warmup):
         barrier()

@@ -103,6 +103,14 @@ int seqalk_job_run(seqalk_job_t *job, void *penalties_dev, void *digests_dev);
 int seqalk_job_set_chunks(seqalk_job_t *job, const int64_t *chunk_ends, int32_t nchunks);
 /* Like seqalk_job_run for one chunk; the pointers address the WHOLE job's result arrays. */
 int seqalk_job_run_chunk(seqalk_job_t *job, int32_t chunk, void *penalties_dev, void *digests_dev);
+/* Asynchronous form of run over all chunks: a library thread enqueues chunk after chunk with
+ * no gap on the GPU.  seqalk_job_wait_chunk returns once chunk c is fully enqueued and makes
+ * consumer_stream (a cudaStream_t of the caller, e.g. the stream its NCCL gather runs on;
+ * NULL = block the host until the results are there) wait for that chunk's results.
+ * seqalk_job_finish_async joins the thread and reports any error. */
+int seqalk_job_start_async(seqalk_job_t *job, void *penalties_dev, void *digests_dev);
+int seqalk_job_wait_chunk(seqalk_job_t *job, int32_t chunk, void *consumer_stream);
+int seqalk_job_finish_async(seqalk_job_t *job);
 /* D2H of the job-owned results. */
 int seqalk_job_fetch(seqalk_job_t *job, int32_t *penalties_out, uint8_t *digests_out);
 int seqalk_job_stats(const seqalk_job_t *job, seqalk_stats_t *stats_out);

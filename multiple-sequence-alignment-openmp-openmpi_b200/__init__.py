@@ -74,6 +74,9 @@ C_ABI = [
     ("seqalk_job_run", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
     ("seqalk_job_set_chunks", _c.c_int, [_c.c_void_p, _I64P, _c.c_int32]),
     ("seqalk_job_run_chunk", _c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p]),
+    ("seqalk_job_start_async", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    ("seqalk_job_wait_chunk", _c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p]),
+    ("seqalk_job_finish_async", _c.c_int, [_c.c_void_p]),
     ("seqalk_job_fetch", _c.c_int, [_c.c_void_p, _I32P, _U8P]),
     ("seqalk_job_stats", _c.c_int, [_c.c_void_p, _c.POINTER(_Stats)]),
     ("seqalk_job_destroy", None, [_c.c_void_p]),
@@ -308,6 +311,18 @@ class Job:
         """run() for one chunk; the device pointers address the whole job's result arrays."""
         _check(lib().seqalk_job_run_chunk(self._h, int(chunk), ctypes.c_void_p(penalties_dev or None),
                                           ctypes.c_void_p(digests_dev or None)))
+
+    def start_async(self, penalties_dev: int = 0, digests_dev: int = 0) -> None:
+        """All chunks back to back, enqueued by a library thread (see wait_chunk)."""
+        _check(lib().seqalk_job_start_async(self._h, ctypes.c_void_p(penalties_dev or None),
+                                            ctypes.c_void_p(digests_dev or None)))
+
+    def wait_chunk(self, chunk: int, consumer_stream: int = 0) -> None:
+        """Order ``consumer_stream`` (raw cudaStream_t, 0 = block the host) after chunk's results."""
+        _check(lib().seqalk_job_wait_chunk(self._h, int(chunk), ctypes.c_void_p(consumer_stream or None)))
+
+    def finish_async(self) -> None:
+        _check(lib().seqalk_job_finish_async(self._h))
 
     def fetch(self) -> Tuple[np.ndarray, np.ndarray]:
         pen = np.zeros(max(self.ntasks, 1), dtype=np.int32)

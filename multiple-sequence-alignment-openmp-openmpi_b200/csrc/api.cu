@@ -185,10 +185,54 @@ void run_tasks(Runtime &r, const SeqPack &pack, const std::vector<TaskIJ> &tasks
 
 }  // namespace
 
+// Idle workers of destroyed jobs, kept with their device buffers so that the next job on the
+// same GPU does not pay cudaMalloc / cudaMallocHost again (a service calls the library many
+// times; the reference's timed region likewise excludes MPI start-up).  seqalk_shutdown()
+// releases them.
+struct WorkerPool {
+  std::mutex mu;
+  std::vector<std::unique_ptr<DeviceWorker>> idle;
+  std::unique_ptr<DeviceWorker> acquire(int device) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (size_t i = 0; i < idle.size(); ++i)
+        if (idle[i]->device() == device) {
+          std::unique_ptr<DeviceWorker> w = std::move(idle[i]);
+          idle.erase(idle.begin() + (long)i);
+          if (w->nslots() == DeviceWorker::slots_from_env()) return w;
+          w.reset();  // configuration changed: free its buffers before building a new one
+          break;
+        }
+    }
+    return std::unique_ptr<DeviceWorker>(new DeviceWorker(device));
+  }
+  void release(std::unique_ptr<DeviceWorker> w) {
+    std::lock_guard<std::mutex> g(mu);
+    idle.push_back(std::move(w));
+  }
+  void clear() {
+    std::lock_guard<std::mutex> g(mu);
+    idle.clear();
+  }
+};
+static WorkerPool &pool() {
+  static WorkerPool p;
+  return p;
+}
+
 struct seqalk_job {
   std::unique_ptr<DeviceWorker> worker;
   std::vector<TaskIJ> tasks;
   int pxy = 0, pgap = 0;
+  ~seqalk_job() {
+    if (worker) {
+      try {
+        worker->finish_async();
+      } catch (...) {
+      }
+      pool().release(std::move(worker));
+    }
+  }
 };
 
 extern "C" {
@@ -208,6 +252,7 @@ void seqalk_shutdown(void) {
   Runtime &r = rt();
   std::lock_guard<std::mutex> g(r.mu);
   r.workers.clear();
+  pool().clear();
 }
 
 int seqalk_device_count(void) {
@@ -351,7 +396,7 @@ int seqalk_job_create(int32_t device, const char *const *seqs, const int32_t *le
       all_tasks(k, tasks);
     }
     std::unique_ptr<seqalk_job> job(new seqalk_job);
-    job->worker.reset(new DeviceWorker(device));
+    job->worker = pool().acquire(device);
     job->worker->load(pack);
     job->worker->plan(tasks, pxy, pgap);
     job->tasks = tasks;
@@ -385,6 +430,36 @@ int seqalk_job_run_chunk(seqalk_job_t *job, int32_t chunk, void *penalties_dev, 
     if (!job || chunk < 0) return fail("bad argument");
     job->worker->run_chunk((size_t)chunk, static_cast<int32_t *>(penalties_dev),
                            static_cast<uint8_t *>(digests_dev));
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_start_async(seqalk_job_t *job, void *penalties_dev, void *digests_dev) {
+  try {
+    if (!job) return fail("null job");
+    job->worker->start_async(static_cast<int32_t *>(penalties_dev), static_cast<uint8_t *>(digests_dev));
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_wait_chunk(seqalk_job_t *job, int32_t chunk, void *consumer_stream) {
+  try {
+    if (!job || chunk < 0) return fail("bad argument");
+    job->worker->wait_chunk((size_t)chunk, static_cast<cudaStream_t>(consumer_stream));
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_job_finish_async(seqalk_job_t *job) {
+  try {
+    if (!job) return fail("null job");
+    job->worker->finish_async();
     return 0;
   } catch (const std::exception &e) {
     return fail(e);

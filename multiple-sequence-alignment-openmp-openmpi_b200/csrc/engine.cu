@@ -126,14 +126,7 @@ DeviceWorker::DeviceWorker(int device) : dev_(device) {
   if (prop.major < 10)
     throw std::runtime_error(std::string("seqalk needs an sm_100a GPU (B200); found ") + prop.name);
   sm_count_ = prop.multiProcessorCount;
-  if (const char *e = std::getenv("SEQALK_SLOTS")) nslots_ = std::max(1, std::min(4, std::atoi(e)));
-  size_t free_b = 0, total_b = 0;
-  SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  double budget_gb = 32.0;
-  if (const char *e = std::getenv("SEQALK_DIR_BUDGET_GB")) budget_gb = std::atof(e);
-  dir_budget_ = (size_t)(budget_gb * (double)(1ull << 30));
-  const size_t cap = (size_t)((double)free_b * 0.80 / nslots_);
-  if (dir_budget_ > cap) dir_budget_ = cap;
+  nslots_ = slots_from_env();
   slots_.resize(nslots_);
   int prio_lo = 0, prio_hi = 0;
   SEQALK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -147,6 +140,12 @@ DeviceWorker::DeviceWorker(int device) : dev_(device) {
   ensure(err_, sizeof(uint32_t));
 }
 
+int DeviceWorker::slots_from_env() {
+  int n = 2;
+  if (const char *e = std::getenv("SEQALK_SLOTS")) n = std::max(1, std::min(4, std::atoi(e)));
+  return n;
+}
+
 void DeviceWorker::release(DevBuf &b) {
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
@@ -154,7 +153,9 @@ void DeviceWorker::release(DevBuf &b) {
 }
 
 DeviceWorker::~DeviceWorker() {
+  if (async_thread_.joinable()) async_thread_.join();
   cudaSetDevice(dev_);
+  for (cudaEvent_t e : chunk_ev_) cudaEventDestroy(e);
   cudaDeviceSynchronize();
   for (Slot &s : slots_) {
     for (DevBuf *b : {&s.pairs, &s.tasks, &s.slots, &s.progress, &s.brow, &s.dirs, &s.out, &s.align, &s.pen,
@@ -239,6 +240,19 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   pgap_ = pgap;
   batches_.clear();
   stats_ = JobStats();
+  {  // direction budget per buffer set: env or 32 GB, capped by the device's memory
+    SEQALK_CUDA(cudaSetDevice(dev_));
+    size_t free_b = 0, total_b = 0;
+    SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    double budget_gb = 32.0;
+    if (const char *e = std::getenv("SEQALK_DIR_BUDGET_GB")) budget_gb = std::atof(e);
+    dir_budget_ = (size_t)(budget_gb * (double)(1ull << 30));
+    // our own (cached) direction buffers count as available
+    size_t own = 0;
+    for (const Slot &s : slots_) own += s.dirs.cap;
+    const size_t cap = (size_t)((double)(free_b + own) * 0.80 / nslots_);
+    if (dir_budget_ > cap) dir_budget_ = cap;
+  }
   // kernel variant
   variant_ = FillVariant();
   variant_.R = 16;  // measured best on B200 (profiles/): 16 rows per lane, cost table when possible
@@ -511,6 +525,21 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     }
     SEQALK_CUDA(cudaEventRecord(S.post_done, st));
     S.post_pending = true;
+    // chunk boundary: mark the chunk's results with an event and tell waiters
+    for (size_t c = 0; c + 1 < chunk_batch_.size(); ++c)
+      if (chunk_batch_[c + 1] == b + 1 && chunk_batch_[c + 1] > chunk_batch_[c]) {
+        while (chunk_ev_.size() <= c) {
+          cudaEvent_t e;
+          SEQALK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          chunk_ev_.push_back(e);
+        }
+        SEQALK_CUDA(cudaEventRecord(chunk_ev_[c], st));
+        {
+          std::lock_guard<std::mutex> g(async_mu_);
+          async_enqueued_ = c + 1;
+        }
+        async_cv_.notify_all();
+      }
     if (streaming) fold_ready(false);  // fold what has landed while the GPU works on later batches
     stats_.fill_launches++;
     stats_.traceback_launches++;
@@ -531,6 +560,56 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   }
   stats_.wall_ms +=
       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+}
+
+void DeviceWorker::start_async(int32_t *penalties_dev, uint8_t *digests_dev) {
+  finish_async();
+  {
+    std::lock_guard<std::mutex> g(async_mu_);
+    async_enqueued_ = 0;
+    async_error_.clear();
+    async_active_ = true;
+  }
+  async_thread_ = std::thread([this, penalties_dev, digests_dev]() {
+    try {
+      run_impl(penalties_dev, digests_dev, nullptr, nullptr, 0, batches_.size());
+    } catch (const std::exception &e) {
+      std::lock_guard<std::mutex> g(async_mu_);
+      async_error_ = e.what();
+      if (async_error_.empty()) async_error_ = "unknown error";
+    }
+    {
+      std::lock_guard<std::mutex> g(async_mu_);
+      async_enqueued_ = chunk_batch_.size();  // releases every waiter (also on error)
+    }
+    async_cv_.notify_all();
+  });
+}
+
+void DeviceWorker::wait_chunk(size_t c, cudaStream_t consumer) {
+  if (c + 1 >= chunk_batch_.size()) throw std::runtime_error("chunk index out of range");
+  {
+    std::unique_lock<std::mutex> lk(async_mu_);
+    async_cv_.wait(lk, [&] { return async_enqueued_ > c; });
+    if (!async_error_.empty()) throw std::runtime_error(async_error_);
+  }
+  if (chunk_batch_[c + 1] == chunk_batch_[c]) return;  // empty chunk
+  SEQALK_CUDA(cudaSetDevice(dev_));
+  if (consumer)
+    SEQALK_CUDA(cudaStreamWaitEvent(consumer, chunk_ev_[c], 0));
+  else
+    SEQALK_CUDA(cudaEventSynchronize(chunk_ev_[c]));
+}
+
+void DeviceWorker::finish_async() {
+  if (async_thread_.joinable()) async_thread_.join();
+  std::string err;
+  {
+    std::lock_guard<std::mutex> g(async_mu_);
+    async_active_ = false;
+    err.swap(async_error_);
+  }
+  if (!err.empty()) throw std::runtime_error(err);
 }
 
 void DeviceWorker::fetch(int32_t *penalties_host, uint8_t *digests_host) {

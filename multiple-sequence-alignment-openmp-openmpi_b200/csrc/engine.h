@@ -9,8 +9,11 @@
 // SM's registers free for it).
 #pragma once
 #include <cuda_runtime.h>
+#include <condition_variable>
 #include <cstdint>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "seqalk_kernels.h"
 
@@ -49,6 +52,8 @@ class DeviceWorker {
   DeviceWorker &operator=(const DeviceWorker &) = delete;
 
   int device() const { return dev_; }
+  int nslots() const { return nslots_; }
+  static int slots_from_env();
   // H2D of the packed sequences (kept resident until the next load()).
   void load(const SeqPack &pack);
   // Plans batches for `tasks`; result slot of tasks[t] is t unless result_slots is given.
@@ -64,6 +69,13 @@ class DeviceWorker {
   // Runs only chunk c (see plan); the pointers address the WHOLE job's result arrays.
   void run_chunk(size_t c, int32_t *penalties_dev = nullptr, uint8_t *digests_dev = nullptr);
   size_t num_chunks() const { return chunk_batch_.empty() ? 0 : chunk_batch_.size() - 1; }
+  // Asynchronous form: a library thread enqueues every chunk back to back (no gap between
+  // chunks on the GPU).  wait_chunk(c, stream) returns once chunk c is fully enqueued and makes
+  // `stream` (a cudaStream_t of the caller, e.g. the one its NCCL gather runs on; null = block
+  // the host instead) wait for the chunk's results.  finish_async() joins and rethrows errors.
+  void start_async(int32_t *penalties_dev, uint8_t *digests_dev);
+  void wait_chunk(size_t c, cudaStream_t consumer);
+  void finish_async();
   // Single-GPU end-to-end path: runs every batch with worker-owned result arrays, copies each
   // batch's results to the host as soon as its digest kernel is done and folds the hash chain
   // (submit/xuliny-seqalkway.cpp:334-337) in task order while later batches are still on the
@@ -122,6 +134,13 @@ class DeviceWorker {
   void run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties, char *fold_hex,
                 size_t batch_begin, size_t batch_end);
   std::vector<size_t> chunk_batch_;  // chunk c = batches [chunk_batch_[c], chunk_batch_[c+1])
+  std::vector<cudaEvent_t> chunk_ev_;  // results of chunk c are in the result arrays
+  std::thread async_thread_;
+  std::mutex async_mu_;
+  std::condition_variable async_cv_;
+  size_t async_enqueued_ = 0;  // chunks fully enqueued by the async thread
+  bool async_active_ = false;
+  std::string async_error_;
   void *h_res_ = nullptr;  // pinned host mirror of the result arrays: T*4 | T*64
   size_t h_res_cap_ = 0;
   std::vector<cudaEvent_t> ev_;

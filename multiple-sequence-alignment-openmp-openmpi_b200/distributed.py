@@ -77,15 +77,25 @@ class GpuShard:
         self.send = [torch.zeros((max(plan.max_count(c), 1), 68), dtype=torch.uint8, device=self.device)
                      for c in range(plan.nchunks)]
 
+    def start(self):
+        """Start every chunk (asynchronously, back to back on the GPU)."""
+        if self.job is not None:
+            self.job.start_async(self.pen.data_ptr(), self.dig.data_ptr())
+
     def run_chunk(self, c: int):
-        """fill + traceback + digest of this rank's tasks of chunk c; returns the send buffer."""
+        """Waits (on torch's current stream, not on the host) for this rank's results of chunk
+        c and packs them into the chunk's send buffer."""
         lo, hi = int(self.starts[c]), int(self.ends[c])
         n = hi - lo
         if n:
-            self.job.run_chunk(c, self.pen.data_ptr(), self.dig.data_ptr())
+            self.job.wait_chunk(c, self.torch.cuda.current_stream(self.device).cuda_stream)
             self.send[c][:n, :4] = self.pen[lo:hi].view(self.torch.uint8).view(n, 4)
             self.send[c][:n, 4:] = self.dig[lo:hi]
         return self.send[c]
+
+    def finish(self):
+        if self.job is not None:
+            self.job.finish_async()
 
     def stats(self):
         return [self.job.stats()] if self.job is not None else []
@@ -168,7 +178,10 @@ def all_pairs_distributed(genes: Sequence[bytes], pxy: int, pgap: int, *, nchunk
         dev = torch.cuda.current_device() if device is None else device
         shard = GpuShard(genes, pxy, pgap, plan, rank, dev)
         try:
-            return run_sharded(plan, rank, shard.run_chunk, group)
+            shard.start()
+            res = run_sharded(plan, rank, shard.run_chunk, group)
+            shard.finish()
+            return res
         finally:
             shard.close()
 
