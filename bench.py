@@ -234,6 +234,7 @@ def main():
         launches += sum(s.fill_launches + s.traceback_launches + s.digest_launches for s in st)
         dir_bytes = sum(s.dir_bytes for s in st)
         my_cells = sum(s.cells for s in st)
+        tile_mode = max((s.tile_mode for s in st), default=0)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     digest_resident = result[0] if rank == 0 else None
@@ -279,6 +280,7 @@ def main():
             "config": {"workload": workloads.CONFIGS[args.workload][0], "name": args.workload, "pxy": pxy,
                        "pgap": pgap, "k": len(genes), "pairs": T, "cells": cells, "sharding": f"lpt-cells x{world}",
                        "gather_chunks": nchunks,
+                       "traceback": "tiles (score-only fill + per-tile recompute)" if tile_mode else "dirs (2-bit directions in HBM)",
                        "l2": "working set (packed directions, GBs per batch) far exceeds the 126 MB L2; no flush needed"},
             "clocks": clocks,
             "e2e": {"value": cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,

@@ -86,6 +86,8 @@ typedef struct seqalk_stats {
   double fill_ms;             /* sum of CUDA-event durations of the fill launches */
   double traceback_ms, digest_ms;
   double wall_ms;             /* host wall time of the last seqalk_job_run */
+  uint32_t tile_mode;         /* 1: score-only fill + tile-recompute traceback, 0: directions in HBM */
+  uint32_t fill_rows_per_lane;
 } seqalk_stats_t;
 
 /* Creates a job on CUDA device `device`: copies the k sequences to the GPU and plans the

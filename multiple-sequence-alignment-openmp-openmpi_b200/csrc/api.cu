@@ -21,6 +21,41 @@ namespace {
 
 thread_local std::string g_last_error;
 
+// Idle workers of destroyed jobs, kept with their device buffers so that the next job on the
+// same GPU does not pay cudaMalloc / cudaMallocHost again (a service calls the library many
+// times; the reference's timed region likewise excludes MPI start-up).  seqalk_shutdown()
+// releases them.
+struct WorkerPool {
+  std::mutex mu;
+  std::vector<std::unique_ptr<DeviceWorker>> idle;
+  std::unique_ptr<DeviceWorker> acquire(int device) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (size_t i = 0; i < idle.size(); ++i)
+        if (idle[i]->device() == device) {
+          std::unique_ptr<DeviceWorker> w = std::move(idle[i]);
+          idle.erase(idle.begin() + (long)i);
+          if (w->nslots() == DeviceWorker::slots_from_env()) return w;
+          w.reset();  // configuration changed: free its buffers before building a new one
+          break;
+        }
+    }
+    return std::unique_ptr<DeviceWorker>(new DeviceWorker(device));
+  }
+  void release(std::unique_ptr<DeviceWorker> w) {
+    std::lock_guard<std::mutex> g(mu);
+    idle.push_back(std::move(w));
+  }
+  void clear() {
+    std::lock_guard<std::mutex> g(mu);
+    idle.clear();
+  }
+};
+static WorkerPool &pool() {
+  static WorkerPool p;
+  return p;
+}
+
 struct Runtime {
   std::mutex mu;
   std::vector<std::unique_ptr<DeviceWorker>> workers;  // devices 0..n-1
@@ -49,8 +84,9 @@ void init_locked(Runtime &r, int ngpus) {
         "no CUDA device visible: libseqalk has no CPU fallback (needs an sm_100a GPU)");
   }
   if (ngpus <= 0 || ngpus > visible) ngpus = visible;
+  for (auto &w : r.workers) pool().release(std::move(w));
   r.workers.clear();
-  for (int d = 0; d < ngpus; ++d) r.workers.emplace_back(new DeviceWorker(d));
+  for (int d = 0; d < ngpus; ++d) r.workers.push_back(pool().acquire(d));
   // fused gather: let every device store its results straight into device 0's arrays
   r.peer_ok = ngpus > 1;
   for (int d = 1; d < ngpus && r.peer_ok; ++d) {
@@ -184,41 +220,6 @@ void run_tasks(Runtime &r, const SeqPack &pack, const std::vector<TaskIJ> &tasks
 }
 
 }  // namespace
-
-// Idle workers of destroyed jobs, kept with their device buffers so that the next job on the
-// same GPU does not pay cudaMalloc / cudaMallocHost again (a service calls the library many
-// times; the reference's timed region likewise excludes MPI start-up).  seqalk_shutdown()
-// releases them.
-struct WorkerPool {
-  std::mutex mu;
-  std::vector<std::unique_ptr<DeviceWorker>> idle;
-  std::unique_ptr<DeviceWorker> acquire(int device) {
-    {
-      std::lock_guard<std::mutex> g(mu);
-      for (size_t i = 0; i < idle.size(); ++i)
-        if (idle[i]->device() == device) {
-          std::unique_ptr<DeviceWorker> w = std::move(idle[i]);
-          idle.erase(idle.begin() + (long)i);
-          if (w->nslots() == DeviceWorker::slots_from_env()) return w;
-          w.reset();  // configuration changed: free its buffers before building a new one
-          break;
-        }
-    }
-    return std::unique_ptr<DeviceWorker>(new DeviceWorker(device));
-  }
-  void release(std::unique_ptr<DeviceWorker> w) {
-    std::lock_guard<std::mutex> g(mu);
-    idle.push_back(std::move(w));
-  }
-  void clear() {
-    std::lock_guard<std::mutex> g(mu);
-    idle.clear();
-  }
-};
-static WorkerPool &pool() {
-  static WorkerPool p;
-  return p;
-}
 
 struct seqalk_job {
   std::unique_ptr<DeviceWorker> worker;
@@ -499,6 +500,8 @@ int seqalk_job_stats(const seqalk_job_t *job, seqalk_stats_t *s) {
   s->traceback_ms = j.traceback_ms;
   s->digest_ms = j.digest_ms;
   s->wall_ms = j.wall_ms;
+  s->tile_mode = j.tile_mode;
+  s->fill_rows_per_lane = j.fill_rows_per_lane;
   return 0;
 }
 

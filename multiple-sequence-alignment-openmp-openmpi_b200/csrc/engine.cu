@@ -258,9 +258,19 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   variant_.R = 16;  // measured best on B200 (profiles/): 16 rows per lane, cost table when possible
   if (const char *e = std::getenv("SEQALK_FILL_R")) variant_.R = std::atoi(e) == 8 ? 8 : 16;
   if (const char *e = std::getenv("SEQALK_FILL_ADD")) variant_.addmode = std::atoi(e) ? 1 : 0;
+  // traceback mode: "tiles" = score-only fill + per-tile recompute (less work per cell, 8x
+  // less memory), "dirs" = 2-bit directions for every cell in HBM.  auto: tiles unless the job
+  // is a handful of pairs (a lone long pair walks its tiles serially on one warp).
+  tiles_ = tasks_.size() >= 8;
+  if (const char *e = std::getenv("SEQALK_TRACEBACK")) {
+    if (!std::strcmp(e, "tiles")) tiles_ = true;
+    if (!std::strcmp(e, "dirs")) tiles_ = false;
+  }
+  if (tiles_) variant_.R = 16;
+  variant_.emit = !tiles_;
   const int R = variant_.R;
   int64_t maxlen = 1;
-  Batch cur{0, 0, 0, 0, 0, 0};
+  Batch cur{0, 0, 0, 0, 0, 0, 0};
   std::vector<size_t> ends;
   if (chunk_ends) ends = *chunk_ends;
   if (ends.empty() || ends.back() != tasks_.size()) ends.push_back(tasks_.size());
@@ -270,7 +280,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     while (next_end < ends.size() && ends[next_end] <= t) {  // chunk boundary: close the batch
       if (cur.count) {
         batches_.push_back(cur);
-        cur = Batch{t, 0, 0, 0, 0, 0};
+        cur = Batch{t, 0, 0, 0, 0, 0, 0};
       }
       chunk_batch_.push_back(batches_.size());
       ++next_end;
@@ -282,14 +292,21 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
       throw std::runtime_error("empty sequence: undefined in the reference (ceil(0/0) tile size, submit/xuliny-seqalkway.cpp:457)");
     maxlen = std::max<int64_t>(maxlen, std::max(m, n));
     const uint32_t ns = (uint32_t)num_strips(m, R);
-    const uint64_t db = (uint64_t)ns * strip_dir_bytes(n, R);
-    if (cur.count && (cur.dir_bytes + db > dir_budget_ || (uint64_t)cur.nstrips + ns > 0x7fffffffull)) {
+    const uint64_t brow_ints = tiles_ ? 2ull * ns * (4ull * (uint64_t)macro_cols(n) + 4)
+                                      : 4ull * (uint64_t)macro_cols(n) + 4;
+    // directions, or (tile mode) the column checkpoints [nq / CKQ][rows padded to the strip]
+    const uint64_t db = tiles_ ? (uint64_t)(macro_cols(n) / CKQ) * ns * (32ull * R) * 4 + 16
+                               : (uint64_t)ns * strip_dir_bytes(n, R);
+    // what counts against the budget: directions, or (tile mode) checkpoints + kept rows
+    const uint64_t bb = tiles_ ? db + brow_ints * 4 : db;
+    if (cur.count && (cur.budget_bytes + bb > dir_budget_ || (uint64_t)cur.nstrips + ns > 0x7fffffffull)) {
       batches_.push_back(cur);
-      cur = Batch{t, 0, 0, 0, 0, 0};
+      cur = Batch{t, 0, 0, 0, 0, 0, 0};
     }
     cur.count++;
     cur.dir_bytes += db;
-    cur.brow_ints += 4ull * (uint64_t)macro_cols(n) + 4;
+    cur.budget_bytes += bb;
+    cur.brow_ints += brow_ints;
     cur.out_bytes += 2ull * round_up((size_t)m + n, 16);
     cur.nstrips += ns;
     stats_.cells += (uint64_t)m * (uint64_t)n;
@@ -313,8 +330,10 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   if (const char *e = std::getenv("SEQALK_FILL_TAB"))
     if (!std::atoi(e)) table = false;
   variant_.mode = general ? MODE_GENERAL : (table ? MODE_TAB : MODE_CMP);
+  stats_.tile_mode = tiles_ ? 1 : 0;
+  stats_.fill_rows_per_lane = (uint32_t)variant_.R;
   // buffer sizes: the largest batch decides, so that run() never reallocates mid-job
-  need_ = Batch{0, 0, 0, 0, 0, 0};
+  need_ = Batch{0, 0, 0, 0, 0, 0, 0};
   for (const Batch &b : batches_) {
     need_.count = std::max(need_.count, b.count);
     need_.dir_bytes = std::max(need_.dir_bytes, b.dir_bytes);
@@ -441,8 +460,13 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       d.task_id = (int32_t)(B.first + p);
       hp[p] = d;
       hs[p] = result_slots_.empty() ? (uint32_t)(B.first + p) : result_slots_[B.first + p];
-      dir_off += (uint64_t)d.nstrips * strip_dir_bytes(d.n, R);
-      brow_off += 4ull * (uint64_t)macro_cols(d.n) + 4;
+      if (tiles_) {
+        dir_off += round_up((uint64_t)(macro_cols(d.n) / CKQ) * d.nstrips * (32ull * R) * 4, 16);
+        brow_off += 2ull * d.nstrips * (4ull * (uint64_t)macro_cols(d.n) + 4);
+      } else {
+        dir_off += (uint64_t)d.nstrips * strip_dir_bytes(d.n, R);
+        brow_off += 4ull * (uint64_t)macro_cols(d.n) + 4;
+      }
       out_off += 2ull * d.cap;
       strip0 += (uint32_t)d.nstrips;
       max_strips = std::max(max_strips, d.nstrips);
@@ -486,8 +510,9 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     SEQALK_CUDA(launch_fill(fa, variant_, sm_count_, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 1], st));
     SEQALK_CUDA(cudaEventRecord(S.fill_done, st));
-    // ---- enqueue: post stream (high priority; runs under the next batch's fill)
-    st = post_stream_;
+    // ---- enqueue: post stream (high priority; runs under the next batch's fill).  In tile
+    // mode the traceback is a heavy kernel of its own: the stages run back to back instead.
+    st = tiles_ ? fill_stream_ : post_stream_;
     SEQALK_CUDA(cudaStreamWaitEvent(st, S.fill_done, 0));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 2], st));
 
@@ -502,7 +527,10 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.pxy = pxy_;
     ta.pgap = pgap_;
     ta.R = R;
-    SEQALK_CUDA(launch_traceback(ta, st));
+    ta.codes = fa.codes;
+    ta.brow = fa.brow;
+    ta.mode = variant_.mode;
+    SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));
 
     DigestArgs da;

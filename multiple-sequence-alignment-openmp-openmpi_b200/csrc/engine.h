@@ -42,6 +42,8 @@ struct JobStats {
   double fill_ms = 0;          // sum of CUDA-event durations of the fill launches
   double traceback_ms = 0, digest_ms = 0;
   double wall_ms = 0;          // host wall time of run()
+  uint32_t tile_mode = 0;      // 1: score-only fill + tile-recompute traceback; 0: directions in HBM
+  uint32_t fill_rows_per_lane = 0;
 };
 
 class DeviceWorker {
@@ -95,6 +97,7 @@ class DeviceWorker {
     size_t first, count;
     uint64_t dir_bytes, brow_ints, out_bytes;
     uint32_t nstrips;
+    uint64_t budget_bytes;
   };
   struct DevBuf {
     void *p = nullptr;
@@ -129,7 +132,8 @@ class DeviceWorker {
   std::vector<Batch> batches_;
   int pxy_ = 0, pgap_ = 0;
   FillVariant variant_;
-  Batch need_{0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches
+  bool tiles_ = false;  // tile mode: score-only fill + checkpoints, directions recomputed per tile
+  Batch need_{0, 0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches
   DevBuf res_pen_, res_dig_, err_;
   void run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties, char *fold_hex,
                 size_t batch_begin, size_t batch_end);

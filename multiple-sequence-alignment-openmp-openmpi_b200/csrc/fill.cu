@@ -30,7 +30,7 @@
 //     a warp's store is one contiguous 512 B segment (strip-major, step-skewed layout).
 #include <cstdlib>
 
-#include "seqalk_kernels.h"
+#include "fill_core.cuh"
 
 namespace seqalk {
 
@@ -50,101 +50,16 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// a + b, optionally forced onto the FMA pipe as a*one + b (one == 1 at run time, unknown
-// to ptxas) so that the ALU pipe is left to VIMNMX3 / SHF / ISETP / PRMT.
-template <int ADDMODE>
-__device__ __forceinline__ int add_i(int a, int b, int one) {
-  if (ADDMODE == 0) return a + b;
-  int r;
-  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
-  return r;
-}
-template <int ADDMODE>
-__device__ __forceinline__ int sub_i(int a, int b, int minus_one) {  // a - b
-  if (ADDMODE == 0) return a - b;
-  int r;
-  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(minus_one), "r"(a));
-  return r;
-}
-
-// One lane's R x 4 block.  h[r] = H' of row r at the previous column; dg = H' of the row
-// above the block at the previous column; up_in[c] = H' of the row above at column c.
-//
-// Per cell, fast modes (pxy >= 0, pgap >= 0, scores far from int32 overflow):
-//     t  = diag + cost(x, y)                           MODE_CMP: ISETP + add + predicated add
-//                                                      MODE_TAB: PRMT (4-letter table) + add
-//     v  = min3(up, left, t)                           VIMNMX3
-//     d1 = v - t      (< 0  <=>  diagonal not optimal) add
-//     d2 = left - up  (< 0  <=>  left strictly better) add
-//     bits = (bits << 1 | sign(d1)) << 1 | sign(d2)    2 funnel shifts (SHF.L.W)
-// On a match the reference takes the diagonal unconditionally (:478-479); with
-// non-negative penalties H[i-1][j-1] <= min(H[i-1][j], H[i][j-1]) + pgap, so the
-// plain minimum selects the same value and sign(d1) = 0 (DIAG) — identical output.
-// MODE_GENERAL (any integers): explicit select on match, compares instead of sign tricks.
-//
-// xc[r]: MODE_TAB: 4 signed bytes, byte q = cost of row r's character against letter q;
-//        otherwise the raw character code (0x100+r for rows past m: never matches).
-template <int R, int MODE, int ADDMODE>
-__device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)[R], const int (&up_in)[4],
-                                           unsigned yword, int A, int B, int one, int minus_one,
-                                           int (&outv)[4], unsigned (&bits)[R / 4]) {
-#pragma unroll
-  for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int yc = (int)((yword >> (8 * c)) & 0xffu);
-    unsigned sel = 0;
-    if (MODE == MODE_TAB) sel = (unsigned)yc * 0x1111u + 0x8880u;  // byte yc, sign-replicated
-    int diag = dg;
-    int up = up_in[c];
-    dg = up;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int w = (c * R + r) / CELLS_PER_WORD;  // cells are shifted in, first cell ends up highest
-      const int left = h[r];
-      int v;
-      if (MODE == MODE_GENERAL) {
-        const bool match = (xc[r] == yc);
-        const int t = diag + B;
-        const int m1 = min(up, left);
-        v = match ? diag + A : min(t, m1);
-        const unsigned nd = ((!match) && (t > m1)) ? 2u : 0u;
-        const unsigned lf = (up > left) ? 1u : 0u;
-        bits[w] = (bits[w] << 2) | nd | lf;
-      } else {
-        int t;
-        if (MODE == MODE_TAB) {
-          int cost;
-          asm("prmt.b32 %0, %1, %2, %3;" : "=r"(cost) : "r"(xc[r]), "r"(0), "r"(sel));
-          t = add_i<ADDMODE>(diag, cost, one);
-        } else {
-          t = add_i<ADDMODE>(diag, B, one);
-          if (ADDMODE == 0)
-            asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p add.s32 %0, %3, %4;}"
-                : "+r"(t)
-                : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A));
-          else
-            asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p mad.lo.s32 %0, %3, %5, %4;}"
-                : "+r"(t)
-                : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A), "r"(one));
-        }
-        v = min(min(up, left), t);
-        const int d1 = sub_i<ADDMODE>(v, t, minus_one);
-        const int d2 = sub_i<ADDMODE>(left, up, minus_one);
-        bits[w] = __funnelshift_l((unsigned)d1, bits[w], 1);
-        bits[w] = __funnelshift_l((unsigned)d2, bits[w], 1);
-      }
-      diag = left;
-      up = v;
-      h[r] = v;
-    }
-    outv[c] = up;
-  }
-}
-
-template <int R, int MODE, int ADDMODE>
+// EMIT = true : directions mode.  2-bit codes for every cell go to HBM (P.dir_off); the boundary
+//               row buffer holds one row per pair, rewritten in place strip after strip.
+// EMIT = false: tile mode.  Scores only; every 256 DP rows (lanes 15 and 31 for R = 16) the row
+//               of H' is kept (P.brow_off: 2 rows per strip), and every CKQ macro columns each
+//               lane stores its R row values (P.dir_off reused as the checkpoint region:
+//               [checkpoint][padded row] int32).  The traceback recomputes directions only for
+//               the 256 x 4*CKQ tiles its path visits (traceback_tiles.cu).
+template <int R, int MODE, int ADDMODE, bool EMIT>
 __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc &P, const int s, const int lane) {
-  constexpr int G = 16 / R;  // macro steps per 16 B direction store
+  constexpr int G = EMIT ? 16 / R : 1;  // macro steps per loop iteration (per 16 B direction store)
   const unsigned FULL = 0xffffffffu;
   const int m = P.m, n = P.n;
   const int nq = (n + 3) >> 2;
@@ -156,7 +71,13 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   const uint8_t *__restrict__ seqbase = (MODE == MODE_TAB) ? a.codes : a.seq;
   const uint8_t *__restrict__ xs = seqbase + P.x_off;
   const unsigned *__restrict__ yw32 = reinterpret_cast<const unsigned *>(seqbase + P.y_off);
-  int4 *__restrict__ brow = reinterpret_cast<int4 *>(a.brow + P.brow_off);
+  // boundary rows: in place (EMIT) or one row per 256 DP rows (tile mode, stride 4*nq+4 ints)
+  const uint64_t bstride = EMIT ? 0 : (uint64_t)(4 * nq + 4);
+  int32_t *bbase = a.brow + P.brow_off;
+  const int4 *__restrict__ brow_rd =
+      reinterpret_cast<const int4 *>(EMIT ? bbase : bbase + (uint64_t)(first ? 0 : 2 * s - 1) * bstride);
+  int4 *__restrict__ brow_wr = reinterpret_cast<int4 *>(
+      EMIT ? bbase : bbase + (uint64_t)(2 * s + (lane == 31 ? 1 : 0)) * bstride);
   uint4 *__restrict__ dout =
       reinterpret_cast<uint4 *>(a.dirs + P.dir_off + (uint64_t)s * ((uint64_t)ngroups * 512ull)) + lane;
   const unsigned *prev_progress = a.progress + P.strip0 + (first ? 0 : s - 1);
@@ -169,15 +90,11 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   for (int r = 0; r < R; ++r) {
     const bool inside = row0 + r < m;
     const int ch = inside ? (int)xs[row0 + r] : 0;
-    if (MODE == MODE_TAB) {
-      const unsigned Ab = (unsigned)A & 0xffu, Bb = (unsigned)B & 0xffu;
-      unsigned tab = Bb * 0x01010101u;
-      if (inside) tab ^= (Ab ^ Bb) << (8 * (ch & 3));
-      xc[r] = (int)tab;
-    } else {
-      xc[r] = inside ? ch : (0x100 + r);
-    }
+    xc[r] = row_operand<MODE>(inside, ch, r, A, B);
   }
+  // tile mode: column checkpoints of this lane's rows, [checkpoint][padded row]
+  const uint64_t mpad = (uint64_t)P.nstrips * (32 * R);
+  int4 *__restrict__ ck_wr = reinterpret_cast<int4 *>(a.dirs + P.dir_off) + (uint64_t)row0 / 4;
 
   int h[R];
 #pragma unroll
@@ -222,7 +139,7 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
         const int qc = g * G + u;
         if (qc < nq) {
           ynext[u] = __ldg(yw32 + qc);
-          if (!first) top[u] = __ldcg(brow + qc);
+          if (!first) top[u] = __ldcg(brow_rd + qc);
         }
       }
     }
@@ -230,7 +147,7 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   fetch_group(0);
 
   for (int g = 0; g < ngroups; ++g) {
-    unsigned pk[4];
+    unsigned pk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int u = 0; u < G; ++u) {
       const int q = g * G + u;
@@ -254,13 +171,27 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
       for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
       if (qc >= 0 && qc < nq) {
         yw = ny;
-        macro_step<R, MODE, ADDMODE>(h, dg, xc, up_in, yw, A, B, one, minus_one, outv, bits);
-        if (lane == 31 && !last) brow[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
-      }
+        macro_step<R, MODE, ADDMODE, EMIT>(h, dg, xc, up_in, yw, A, B, one, minus_one, outv, bits);
+        if (EMIT) {
+          if (lane == 31 && !last) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
+        } else {
+          // every 256 rows (R = 16: lanes 15 and 31) keep the row for the tile traceback
+          if ((lane & (256 / R - 1)) == (256 / R - 1)) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
+          // column checkpoint: H' of this lane's rows at the last column of macro col qc
+          if (((qc + 1) & (CKQ - 1)) == 0) {
+            int4 *dst = ck_wr + ((uint64_t)((qc + 1) / CKQ - 1) * mpad) / 4;
 #pragma unroll
-      for (int w = 0; w < R / 4; ++w) pk[u * (R / 4) + w] = bits[w];
+            for (int r4 = 0; r4 < R / 4; ++r4)
+              dst[r4] = make_int4(h[4 * r4], h[4 * r4 + 1], h[4 * r4 + 2], h[4 * r4 + 3]);
+          }
+        }
+      }
+      if (EMIT) {
+#pragma unroll
+        for (int w = 0; w < R / 4; ++w) pk[u * (R / 4) + w] = bits[w];
+      }
     }
-    dout[(size_t)g * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    if (EMIT) dout[(size_t)g * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 
     // publish progress of the bottom row (lane 31 trails by 31 macro steps)
     if (!last) {
@@ -275,7 +206,7 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   }
 }
 
-template <int R, int MODE, int ADDMODE>
+template <int R, int MODE, int ADDMODE, bool EMIT>
 __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillArgs a) {
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -285,18 +216,27 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillArgs a) {
     if (t >= a.ntasks) break;
     const StripTask task = a.tasks[t];
     const PairDesc P = a.pairs[task.pair];
-    process_strip<R, MODE, ADDMODE>(a, P, (int)task.strip, lane);
+    process_strip<R, MODE, ADDMODE, EMIT>(a, P, (int)task.strip, lane);
   }
 }
 
 typedef void (*FillKernelPtr)(const FillArgs);
 
 static FillKernelPtr pick_kernel(const FillVariant &v) {
+  if (!v.emit) {  // tile mode: R = 16 only
+    if (v.R != 16) return nullptr;
+    if (v.mode == MODE_GENERAL) return fill_kernel<16, MODE_GENERAL, 0, false>;
+    if (v.mode == MODE_CMP) return v.addmode ? fill_kernel<16, MODE_CMP, 1, false> : fill_kernel<16, MODE_CMP, 0, false>;
+    if (v.mode == MODE_TAB) return v.addmode ? fill_kernel<16, MODE_TAB, 1, false> : fill_kernel<16, MODE_TAB, 0, false>;
+    return nullptr;
+  }
 #define SEQALK_PICK(RR)                                                                     \
   if (v.R == RR) {                                                                          \
-    if (v.mode == MODE_GENERAL) return fill_kernel<RR, MODE_GENERAL, 0>;                    \
-    if (v.mode == MODE_CMP) return v.addmode ? fill_kernel<RR, MODE_CMP, 1> : fill_kernel<RR, MODE_CMP, 0>; \
-    if (v.mode == MODE_TAB) return v.addmode ? fill_kernel<RR, MODE_TAB, 1> : fill_kernel<RR, MODE_TAB, 0>; \
+    if (v.mode == MODE_GENERAL) return fill_kernel<RR, MODE_GENERAL, 0, true>;              \
+    if (v.mode == MODE_CMP)                                                                 \
+      return v.addmode ? fill_kernel<RR, MODE_CMP, 1, true> : fill_kernel<RR, MODE_CMP, 0, true>; \
+    if (v.mode == MODE_TAB)                                                                 \
+      return v.addmode ? fill_kernel<RR, MODE_TAB, 1, true> : fill_kernel<RR, MODE_TAB, 0, true>; \
   }
   SEQALK_PICK(8)
   SEQALK_PICK(16)
@@ -304,16 +244,17 @@ static FillKernelPtr pick_kernel(const FillVariant &v) {
   return nullptr;
 }
 
-// Resident fill CTAs per SM.  The fill is a persistent kernel; it must leave room for the
-// small traceback / digest CTAs of the previous batch (<= 64 threads x 64 registers), which
-// run concurrently on the high-priority stream: keep >= 4096 registers of every SM free.
+// Resident fill CTAs per SM.  In directions mode the fill is a persistent kernel that must
+// leave room for the small traceback / digest CTAs of the previous batch (<= 64 threads x 64
+// registers), which run concurrently on the high-priority stream: keep >= 4096 registers of
+// every SM free.  In tile mode the stages run one after the other: no headroom.
 int fill_blocks_per_sm(const FillVariant &v) {
   FillKernelPtr k = pick_kernel(v);
   if (!k) return 0;
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, FILL_THREADS, 0);
   cudaFuncAttributes attr;
-  if (cudaFuncGetAttributes(&attr, k) == cudaSuccess) {
+  if (v.emit && cudaFuncGetAttributes(&attr, k) == cudaSuccess) {
     const int regs_alloc = (attr.numRegs + 7) / 8 * 8;
     int headroom = 4096;
     if (const char *e = getenv("SEQALK_FILL_HEADROOM_REGS")) headroom = atoi(e);

@@ -1,0 +1,119 @@
+// fill_core.cuh — the per-lane R x 4 block update shared by the fill kernels (fill.cu) and the
+// tile-recompute traceback (traceback_tiles.cu).  See fill.cu for the decomposition.
+#pragma once
+#include "seqalk_kernels.h"
+
+namespace seqalk {
+
+// a + b, optionally forced onto the FMA pipe as a*one + b (one == 1 at run time, unknown
+// to ptxas) so that the ALU pipe is left to VIMNMX3 / SHF / ISETP / PRMT.
+template <int ADDMODE>
+__device__ __forceinline__ int add_i(int a, int b, int one) {
+  if (ADDMODE == 0) return a + b;
+  int r;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+  return r;
+}
+template <int ADDMODE>
+__device__ __forceinline__ int sub_i(int a, int b, int minus_one) {  // a - b
+  if (ADDMODE == 0) return a - b;
+  int r;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(minus_one), "r"(a));
+  return r;
+}
+
+// One lane's R x 4 block.  h[r] = H' of row r at the previous column; dg = H' of the row
+// above the block at the previous column; up_in[c] = H' of the row above at column c.
+//
+// Per cell, fast modes (pxy >= 0, pgap >= 0, scores far from int32 overflow):
+//     t  = diag + cost(x, y)                           MODE_CMP: ISETP + add + predicated add
+//                                                      MODE_TAB: PRMT (4-letter table) + add
+//     v  = min3(up, left, t)                           VIMNMX3
+//     d1 = v - t      (< 0  <=>  diagonal not optimal) add
+//     d2 = left - up  (< 0  <=>  left strictly better) add
+//     bits = (bits << 1 | sign(d1)) << 1 | sign(d2)    2 funnel shifts (SHF.L.W)
+// On a match the reference takes the diagonal unconditionally (:478-479); with
+// non-negative penalties H[i-1][j-1] <= min(H[i-1][j], H[i][j-1]) + pgap, so the
+// plain minimum selects the same value and sign(d1) = 0 (DIAG) — identical output.
+// MODE_GENERAL (any integers): explicit select on match, compares instead of sign tricks.
+//
+// xc[r]: MODE_TAB: 4 signed bytes, byte q = cost of row r's character against letter q;
+//        otherwise the raw character code (0x100+r for rows past m: never matches).
+// EMIT = false: scores only (no direction bits): the checkpointed fill of the tile mode.
+template <int R, int MODE, int ADDMODE, bool EMIT>
+__device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)[R], const int (&up_in)[4],
+                                           unsigned yword, int A, int B, int one, int minus_one,
+                                           int (&outv)[4], unsigned (&bits)[R / 4]) {
+#pragma unroll
+  for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int yc = (int)((yword >> (8 * c)) & 0xffu);
+    unsigned sel = 0;
+    if (MODE == MODE_TAB) sel = (unsigned)yc * 0x1111u + 0x8880u;  // byte yc, sign-replicated
+    int diag = dg;
+    int up = up_in[c];
+    dg = up;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int w = (c * R + r) / CELLS_PER_WORD;  // cells are shifted in, first cell ends up highest
+      const int left = h[r];
+      int v;
+      if (MODE == MODE_GENERAL) {
+        const bool match = (xc[r] == yc);
+        const int t = diag + B;
+        const int m1 = min(up, left);
+        v = match ? diag + A : min(t, m1);
+        if (EMIT) {
+          const unsigned nd = ((!match) && (t > m1)) ? 2u : 0u;
+          const unsigned lf = (up > left) ? 1u : 0u;
+          bits[w] = (bits[w] << 2) | nd | lf;
+        }
+      } else {
+        int t;
+        if (MODE == MODE_TAB) {
+          int cost;
+          asm("prmt.b32 %0, %1, %2, %3;" : "=r"(cost) : "r"(xc[r]), "r"(0), "r"(sel));
+          t = add_i<ADDMODE>(diag, cost, one);
+        } else {
+          t = add_i<ADDMODE>(diag, B, one);
+          if (ADDMODE == 0)
+            asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p add.s32 %0, %3, %4;}"
+                : "+r"(t)
+                : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A));
+          else
+            asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p mad.lo.s32 %0, %3, %5, %4;}"
+                : "+r"(t)
+                : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A), "r"(one));
+        }
+        v = min(min(up, left), t);
+        if (EMIT) {
+          const int d1 = sub_i<ADDMODE>(v, t, minus_one);
+          const int d2 = sub_i<ADDMODE>(left, up, minus_one);
+          bits[w] = __funnelshift_l((unsigned)d1, bits[w], 1);
+          bits[w] = __funnelshift_l((unsigned)d2, bits[w], 1);
+        }
+      }
+      diag = left;
+      up = v;
+      h[r] = v;
+    }
+    outv[c] = up;
+  }
+}
+
+
+// Row operand of macro_step for one DP row: the 4-letter cost table (MODE_TAB, `ch` is a letter
+// code 0..3) or the raw character; rows past the end of x never match.
+template <int MODE>
+__device__ __forceinline__ int row_operand(bool inside, int ch, int r, int A, int B) {
+  if (MODE == MODE_TAB) {
+    const unsigned Ab = (unsigned)A & 0xffu, Bb = (unsigned)B & 0xffu;
+    unsigned tab = Bb * 0x01010101u;
+    if (inside) tab ^= (Ab ^ Bb) << (8 * (ch & 3));
+    return (int)tab;
+  }
+  return inside ? ch : (0x100 + r);
+}
+
+}  // namespace seqalk

@@ -12,7 +12,12 @@ struct FillVariant {
   int R = 8;        // DP rows per lane (8 or 16); strip = 32*R rows
   int mode = MODE_CMP;
   int addmode = 0;  // 1: adds forced onto the FMA pipe (IMAD)
+  bool emit = true; // true: directions mode (2-bit codes to HBM); false: tile mode (scores +
+                    // checkpoints, directions recomputed by the traceback for the tiles it visits)
 };
+// tile mode: a column checkpoint every CKQ macro columns (4*CKQ DP columns), a row every 256 rows
+constexpr int CKQ = 64;
+constexpr int TILE_ROWS = 256;
 // bottom-row progress is published every PUBLISH_EVERY macro columns (and at strip end)
 constexpr int PUBLISH_EVERY = 64;
 constexpr int TRACEBACK_THREADS = 32;
@@ -36,6 +41,9 @@ struct FillArgs {
 
 struct TracebackArgs {
   const uint8_t *seq;
+  const uint8_t *codes;     // letters remapped to 0..3 (tile mode with MODE_TAB), else null
+  const int32_t *brow;      // tile mode: kept boundary rows (one per 256 DP rows)
+  int32_t mode;             // tile mode: MODE_* of the recompute (same arithmetic as the fill)
   const PairDesc *pairs;
   uint32_t npairs;
   const uint8_t *dirs;
@@ -61,6 +69,7 @@ struct DigestArgs {
 cudaError_t launch_fill(const FillArgs &args, const FillVariant &v, int sm_count, cudaStream_t stream);
 int fill_blocks_per_sm(const FillVariant &v);
 cudaError_t launch_traceback(const TracebackArgs &args, cudaStream_t stream);
+cudaError_t launch_traceback_tiles(const TracebackArgs &args, cudaStream_t stream);
 cudaError_t launch_digest(const DigestArgs &args, cudaStream_t stream);
 
 }  // namespace seqalk

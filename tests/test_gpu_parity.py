@@ -158,7 +158,7 @@ def test_batching_does_not_change_results(seqalk, oracle, workloads, monkeypatch
     with seqalk.Job(genes, 3, 2) as job:
         job.run()
         assert job.stats().batches == 1
-    monkeypatch.setenv("SEQALK_DIR_BUDGET_GB", "0.002")  # ~2 MB of directions per batch
+    monkeypatch.setenv("SEQALK_DIR_BUDGET_GB", "0.0005")  # ~0.5 MB of checkpoints/directions per batch
     with seqalk.Job(genes, 3, 2) as job:
         job.run()
         pen, dig = job.fetch()
@@ -250,6 +250,13 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     {"SEQALK_FILL_R": "16", "SEQALK_FILL_TAB": "0", "SEQALK_FILL_ADD": "1"},
     {"SEQALK_FILL_R": "16", "SEQALK_FORCE_GENERAL": "1"},
     {"SEQALK_FILL_R": "8", "SEQALK_SLOTS": "1"},
+    {"SEQALK_TRACEBACK": "dirs"},
+    {"SEQALK_TRACEBACK": "dirs", "SEQALK_FILL_R": "8", "SEQALK_FILL_TAB": "0"},
+    {"SEQALK_TRACEBACK": "tiles"},
+    {"SEQALK_TRACEBACK": "tiles", "SEQALK_FILL_TAB": "0"},
+    {"SEQALK_TRACEBACK": "tiles", "SEQALK_FILL_TAB": "0", "SEQALK_FILL_ADD": "1"},
+    {"SEQALK_TRACEBACK": "tiles", "SEQALK_FORCE_GENERAL": "1"},
+    {"SEQALK_TRACEBACK": "tiles", "SEQALK_DIR_BUDGET_GB": "0.001"},
 ], ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
 def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatch, env):
     """Rows per lane (8/16), cost by compare or by 4-letter table, adds on ALU or FMA pipe,
@@ -298,3 +305,28 @@ def test_two_gpus_in_process_match_one_gpu(seqalk, oracle, workloads):
         seqalk.init(1)
     assert d2 == od and np.array_equal(p2, op)
     assert d2b == od and np.array_equal(p2b, op)
+
+
+@pytest.mark.parametrize("mode", ["tiles", "dirs"])
+def test_traceback_modes_on_long_and_skewed_pairs(seqalk, oracle, workloads, monkeypatch, mode):
+    """Both traceback modes (directions in HBM / per-tile recompute from checkpoints) on pairs
+    that cross many 256-row and 256-column tile edges, incl. very unequal lengths and a
+    substring pair (long pure-gap runs along a tile edge)."""
+    monkeypatch.setenv("SEQALK_TRACEBACK", mode)
+    rnd = random.Random(23)
+    base = bytes(rnd.choice(b"ACGT") for _ in range(6000))
+    genes = [base, base[700:5200], bytes(rnd.choice(b"ACGT") for _ in range(5000)),
+             bytes(rnd.choice(b"ACGT") for _ in range(300)), bytes(rnd.choice(b"ACGT") for _ in range(2049)),
+             bytes(rnd.choice(b"ACGT") for _ in range(257)), base[::-1][:3000]]
+    with seqalk.Job(genes, 3, 2) as job:
+        job.run()
+        pen, dig = job.fetch()
+        assert job.stats().tile_mode == (1 if mode == "tiles" else 0)
+    od, op, oh = oracle.all_pairs(genes, 3, 2, want_pair_hashes=True)
+    assert np.array_equal(pen, op)
+    assert [d.tobytes().hex() for d in dig] == oh
+    # one long pair through getMinimumPenalty (arrays) in this mode
+    x, y = genes[0], genes[2]
+    pen1, xans, yans = seqalk.get_minimum_penalty(x, y, 3, 2)
+    open_, a1, a2, _ = oracle.pair(x, y, 3, 2)
+    assert pen1 == open_ and seqalk.alignment_strings(xans, yans) == (a1, a2)
