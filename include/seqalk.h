@@ -130,9 +130,11 @@ int seqalk_sha512_hex(const void *data, size_t len, char out[129]);
 /* Dependent-free issue-rate microbenchmarks on `device`, in lane-operations per second:
  * [0] LOP3 (ALU pipe), [1] VIMNMX3 (3-input min), [2] IMAD (FMA pipe), [3] LOP3+IMAD
  * alternating (dual pipe), [4] VIADDMNMX (fused add+min), [5] SHF (funnel shift),
- * [6] LOP3+VIMNMX3 alternating, [7] the fill kernel's mix (1 VIMNMX3 : 1 SHF : 2 IMAD).
+ * [6] LOP3+VIMNMX3 alternating, [7] the directions-mode fill mix (1 VIMNMX3 : 1 SHF : 2 IMAD),
+ * [8] IDP.4A (byte dot product + add), [9] IDP.4A+VIMNMX3 alternating, [10] IDP.4A+IMAD
+ * alternating, [11] PRMT.
  * rates_out[0] is the integer-ALU roofline denominator of SURVEY.md section 8d. */
-int seqalk_measure_int_peaks(int32_t device, double rates_out[8]);
+int seqalk_measure_int_peaks(int32_t device, double rates_out[12]);
 
 #ifdef __cplusplus
 }

@@ -362,12 +362,13 @@ def fold_chain(pair_digests: np.ndarray, state: str = "") -> str:
     return buf.value.decode("ascii")
 
 
-INT_PEAK_NAMES = ["lop3", "vimnmx3", "imad", "lop3+imad", "viaddmnmx", "shf", "lop3+vimnmx3", "fill_mix"]
+INT_PEAK_NAMES = ["lop3", "vimnmx3", "imad", "lop3+imad", "viaddmnmx", "shf", "lop3+vimnmx3", "fill_mix",
+                  "idp4a", "idp4a+vimnmx3", "idp4a+imad", "prmt"]
 
 
 def measure_int_peaks(device: int = 0) -> dict:
     """Issue-rate microbenchmarks (lane-ops/s) — the integer roofline denominators."""
-    r = (ctypes.c_double * 8)()
+    r = (ctypes.c_double * 12)()
     if lib().seqalk_measure_int_peaks(int(device), r) != 0:
         raise SeqalkError("seqalk_measure_int_peaks failed (no usable GPU?)")
     return dict(zip(INT_PEAK_NAMES, [float(v) for v in r]))

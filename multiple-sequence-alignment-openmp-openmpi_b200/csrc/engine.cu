@@ -46,7 +46,7 @@ void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
       const uint8_t ch = (uint8_t)seqs[i][c];
       if (!seen[ch]) {
         seen[ch] = true;
-        if (nletters < 4) code_of[ch] = (uint8_t)nletters;
+        if (nletters < 4) code_of[ch] = (uint8_t)(8 * nletters);  // stored as the byte's bit offset
         if (++nletters > 4) break;
       }
     }
@@ -256,8 +256,9 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   // kernel variant
   variant_ = FillVariant();
   variant_.R = 16;  // measured best on B200 (profiles/): 16 rows per lane, cost table when possible
+  variant_.addmode = 2;  // cost table lookup + add as one IDP.4A (FMA pipe) when the table applies
   if (const char *e = std::getenv("SEQALK_FILL_R")) variant_.R = std::atoi(e) == 8 ? 8 : 16;
-  if (const char *e = std::getenv("SEQALK_FILL_ADD")) variant_.addmode = std::atoi(e) ? 1 : 0;
+  if (const char *e = std::getenv("SEQALK_FILL_ADD")) variant_.addmode = std::max(0, std::min(2, std::atoi(e)));
   // traceback mode: "tiles" = score-only fill + per-tile recompute (less work per cell, 8x
   // less memory), "dirs" = 2-bit directions for every cell in HBM.  auto: tiles unless the job
   // is a handful of pairs (a lone long pair walks its tiles serially on one warp).
@@ -530,6 +531,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.codes = fa.codes;
     ta.brow = fa.brow;
     ta.mode = variant_.mode;
+    ta.addmode = variant_.addmode;
     SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));
 

@@ -25,7 +25,7 @@ struct SeqPack {
   std::vector<uint8_t> bytes;
   std::vector<uint32_t> off;
   std::vector<int32_t> len;
-  std::vector<uint8_t> codes;  // same layout as bytes with letters remapped to 0..3; empty if > 4 letters
+  std::vector<uint8_t> codes;  // same layout as bytes, letters remapped to 8*(0..3); empty if > 4 letters
   int k = 0;
   void build(const char *const *seqs, const int32_t *lens, int k);
 };

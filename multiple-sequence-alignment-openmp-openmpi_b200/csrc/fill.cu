@@ -59,7 +59,7 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 //               the 256 x 4*CKQ tiles its path visits (traceback_tiles.cu).
 template <int R, int MODE, int ADDMODE, bool EMIT>
 __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc &P, const int s, const int lane) {
-  constexpr int G = EMIT ? 16 / R : 1;  // macro steps per loop iteration (per 16 B direction store)
+  constexpr int G = EMIT ? 16 / R : 2;  // macro steps per loop iteration (per 16 B direction store)
   const unsigned FULL = 0xffffffffu;
   const int m = P.m, n = P.n;
   const int nq = (n + 3) >> 2;
@@ -227,7 +227,10 @@ static FillKernelPtr pick_kernel(const FillVariant &v) {
     if (v.R != 16) return nullptr;
     if (v.mode == MODE_GENERAL) return fill_kernel<16, MODE_GENERAL, 0, false>;
     if (v.mode == MODE_CMP) return v.addmode ? fill_kernel<16, MODE_CMP, 1, false> : fill_kernel<16, MODE_CMP, 0, false>;
-    if (v.mode == MODE_TAB) return v.addmode ? fill_kernel<16, MODE_TAB, 1, false> : fill_kernel<16, MODE_TAB, 0, false>;
+    if (v.mode == MODE_TAB) {
+      if (v.addmode == 2) return fill_kernel<16, MODE_TAB, 2, false>;
+      return v.addmode ? fill_kernel<16, MODE_TAB, 1, false> : fill_kernel<16, MODE_TAB, 0, false>;
+    }
     return nullptr;
   }
 #define SEQALK_PICK(RR)                                                                     \
@@ -238,6 +241,7 @@ static FillKernelPtr pick_kernel(const FillVariant &v) {
     if (v.mode == MODE_TAB)                                                                 \
       return v.addmode ? fill_kernel<RR, MODE_TAB, 1, true> : fill_kernel<RR, MODE_TAB, 0, true>; \
   }
+  if (v.R == 16 && v.mode == MODE_TAB && v.addmode == 2) return fill_kernel<16, MODE_TAB, 2, true>;
   SEQALK_PICK(8)
   SEQALK_PICK(16)
 #undef SEQALK_PICK

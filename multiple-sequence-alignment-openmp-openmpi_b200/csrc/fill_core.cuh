@@ -9,14 +9,14 @@ namespace seqalk {
 // to ptxas) so that the ALU pipe is left to VIMNMX3 / SHF / ISETP / PRMT.
 template <int ADDMODE>
 __device__ __forceinline__ int add_i(int a, int b, int one) {
-  if (ADDMODE == 0) return a + b;
+  if (ADDMODE != 1) return a + b;
   int r;
   asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
   return r;
 }
 template <int ADDMODE>
 __device__ __forceinline__ int sub_i(int a, int b, int minus_one) {  // a - b
-  if (ADDMODE == 0) return a - b;
+  if (ADDMODE != 1) return a - b;
   int r;
   asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(minus_one), "r"(a));
   return r;
@@ -48,9 +48,16 @@ __device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)
   for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const int yc = (int)((yword >> (8 * c)) & 0xffu);
+    int yc = 0;
     unsigned sel = 0;
-    if (MODE == MODE_TAB) sel = (unsigned)yc * 0x1111u + 0x8880u;  // byte yc, sign-replicated
+    if (MODE == MODE_TAB && ADDMODE == 2) {
+      // y letters arrive as shift amounts 8*code: one funnel shift (amount mod 32) builds the
+      // one-hot byte mask; dp4a(table, one-hot, diag) = diag + table[code]
+      sel = __funnelshift_l(0u, 1u, yword >> (8 * c));
+    } else {
+      yc = (int)((yword >> (8 * c)) & 0xffu);
+      if (MODE == MODE_TAB) sel = (unsigned)(yc >> 3) * 0x1111u + 0x8880u;  // PRMT: byte code, sign-replicated
+    }
     int diag = dg;
     int up = up_in[c];
     dg = up;
@@ -71,7 +78,10 @@ __device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)
         }
       } else {
         int t;
-        if (MODE == MODE_TAB) {
+        if (MODE == MODE_TAB && ADDMODE == 2) {
+          // cost lookup and add in ONE instruction (IDP.4A): sum of table bytes x one-hot bytes
+          t = __dp4a(xc[r], (int)sel, diag);
+        } else if (MODE == MODE_TAB) {
           int cost;
           asm("prmt.b32 %0, %1, %2, %3;" : "=r"(cost) : "r"(xc[r]), "r"(0), "r"(sel));
           t = add_i<ADDMODE>(diag, cost, one);
@@ -103,14 +113,14 @@ __device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)
 }
 
 
-// Row operand of macro_step for one DP row: the 4-letter cost table (MODE_TAB, `ch` is a letter
-// code 0..3) or the raw character; rows past the end of x never match.
+// Row operand of macro_step for one DP row: the 4-letter cost table (MODE_TAB, `ch` is 8 x the
+// letter code, i.e. 0/8/16/24) or the raw character; rows past the end of x never match.
 template <int MODE>
 __device__ __forceinline__ int row_operand(bool inside, int ch, int r, int A, int B) {
   if (MODE == MODE_TAB) {
     const unsigned Ab = (unsigned)A & 0xffu, Bb = (unsigned)B & 0xffu;
     unsigned tab = Bb * 0x01010101u;
-    if (inside) tab ^= (Ab ^ Bb) << (8 * (ch & 3));
+    if (inside) tab ^= (Ab ^ Bb) << (ch & 24);  // ch = 8 * letter code
     return (int)tab;
   }
   return inside ? ch : (0x100 + r);

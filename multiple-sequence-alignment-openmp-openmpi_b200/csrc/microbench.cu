@@ -9,7 +9,8 @@
 
 namespace {
 
-enum Kind { K_LOP3 = 0, K_MIN3 = 1, K_IMAD = 2, K_MIXED = 3, K_ADDMIN = 4, K_SHF = 5, K_ALUMIN = 6, K_FILLMIX = 7 };
+enum Kind { K_LOP3 = 0, K_MIN3 = 1, K_IMAD = 2, K_MIXED = 3, K_ADDMIN = 4, K_SHF = 5, K_ALUMIN = 6, K_FILLMIX = 7,
+            K_DP4A = 8, K_DP4A_MIN3 = 9, K_DP4A_IMAD = 10, K_PRMT = 11 };
 
 template <int KIND>
 __global__ void __launch_bounds__(256) issue_kernel(int *out, int iters, int a, int b) {
@@ -18,6 +19,8 @@ __global__ void __launch_bounds__(256) issue_kernel(int *out, int iters, int a, 
 #define MIN3(r) asm volatile("{.reg .s32 t; min.s32 t, %0, %1; min.s32 %0, t, %2;}" : "+r"(r) : "r"(a), "r"(b))
 #define ADDMIN(r) asm volatile("{.reg .s32 t; add.s32 t, %0, %2; min.s32 %0, t, %1;}" : "+r"(r) : "r"(a), "r"(b))
 #define SHF(r) asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(r) : "r"(a))
+#define DP4A(r) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b))
+#define PRMT(r) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(r) : "r"(a), "r"(b))
 #define MAD(r) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(r) : "r"(a), "r"(b))
 #define ROW(OP) OP(r0); OP(r1); OP(r2); OP(r3); OP(r4); OP(r5); OP(r6); OP(r7)
   for (int i = 0; i < iters; ++i) {
@@ -29,6 +32,10 @@ __global__ void __launch_bounds__(256) issue_kernel(int *out, int iters, int a, 
     if (KIND == K_SHF) { ROW(SHF); ROW(SHF); ROW(SHF); ROW(SHF); }
     if (KIND == K_ALUMIN) { ROW(ALU); ROW(MIN3); ROW(ALU); ROW(MIN3); }
     if (KIND == K_FILLMIX) { ROW(MIN3); ROW(SHF); ROW(MAD); ROW(MAD); }
+    if (KIND == K_DP4A) { ROW(DP4A); ROW(DP4A); ROW(DP4A); ROW(DP4A); }
+    if (KIND == K_DP4A_MIN3) { ROW(DP4A); ROW(MIN3); ROW(DP4A); ROW(MIN3); }
+    if (KIND == K_DP4A_IMAD) { ROW(DP4A); ROW(MAD); ROW(DP4A); ROW(MAD); }
+    if (KIND == K_PRMT) { ROW(PRMT); ROW(PRMT); ROW(PRMT); ROW(PRMT); }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
 }
@@ -59,7 +66,7 @@ double run_kind(int sm_count, int *d_out) {
 
 }  // namespace
 
-extern "C" int seqalk_measure_int_peaks(int32_t device, double rates_out[8]) {
+extern "C" int seqalk_measure_int_peaks(int32_t device, double rates_out[12]) {
   if (!rates_out) return 1;
   if (cudaSetDevice(device) != cudaSuccess) return 1;
   cudaDeviceProp prop;
@@ -75,6 +82,10 @@ extern "C" int seqalk_measure_int_peaks(int32_t device, double rates_out[8]) {
   rates_out[5] = run_kind<K_SHF>(sms, d_out);
   rates_out[6] = run_kind<K_ALUMIN>(sms, d_out);
   rates_out[7] = run_kind<K_FILLMIX>(sms, d_out);
+  rates_out[8] = run_kind<K_DP4A>(sms, d_out);
+  rates_out[9] = run_kind<K_DP4A_MIN3>(sms, d_out);
+  rates_out[10] = run_kind<K_DP4A_IMAD>(sms, d_out);
+  rates_out[11] = run_kind<K_PRMT>(sms, d_out);
   cudaFree(d_out);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -11,7 +11,7 @@ enum : int { MODE_GENERAL = 0, MODE_CMP = 1, MODE_TAB = 2 };
 struct FillVariant {
   int R = 8;        // DP rows per lane (8 or 16); strip = 32*R rows
   int mode = MODE_CMP;
-  int addmode = 0;  // 1: adds forced onto the FMA pipe (IMAD)
+  int addmode = 0;  // 1: adds forced onto the FMA pipe (IMAD); 2: MODE_TAB lookup+add as one IDP.4A
   bool emit = true; // true: directions mode (2-bit codes to HBM); false: tile mode (scores +
                     // checkpoints, directions recomputed by the traceback for the tiles it visits)
 };
@@ -27,7 +27,7 @@ constexpr int BUFFER_SLACK = 64;
 
 struct FillArgs {
   const uint8_t *seq;       // packed sequences (each 16 B aligned, zero padded)
-  const uint8_t *codes;     // same layout, letters remapped to 0..3 (MODE_TAB only, else null)
+  const uint8_t *codes;     // same layout, letters remapped to 8*(0..3) (MODE_TAB only, else null)
   const PairDesc *pairs;    // pairs of this batch
   const StripTask *tasks;   // strip queue, ordered (strip, pair)
   uint32_t ntasks;
@@ -44,6 +44,7 @@ struct TracebackArgs {
   const uint8_t *codes;     // letters remapped to 0..3 (tile mode with MODE_TAB), else null
   const int32_t *brow;      // tile mode: kept boundary rows (one per 256 DP rows)
   int32_t mode;             // tile mode: MODE_* of the recompute (same arithmetic as the fill)
+  int32_t addmode;          // tile mode: 2 = IDP.4A cost lookup in the recompute
   const PairDesc *pairs;
   uint32_t npairs;
   const uint8_t *dirs;

@@ -46,7 +46,7 @@ struct BackWriter0 {
 
 }  // namespace
 
-template <int MODE>
+template <int MODE, int ADDMODE>
 __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs a) {
   extern __shared__ uint2 sdirs[];  // [CKQ][32]: codes of the tile's macro column qc, lane t
   const unsigned FULL = 0xffffffffu;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
       if (qc >= 0 && qc < tq && lane <= tmax) {
         yw = ny;
         unsigned bits[RT / 4];
-        macro_step<RT, MODE, 0, true>(h, dg, xc, up_in, yw, A, B, 1, -1, outv, bits);
+        macro_step<RT, MODE, ADDMODE, true>(h, dg, xc, up_in, yw, A, B, 1, -1, outv, bits);
         sdirs[qc * 32 + lane] = make_uint2(bits[0], bits[1]);
       }
     }
@@ -189,9 +189,14 @@ cudaError_t launch_traceback_tiles(const TracebackArgs &args, cudaStream_t strea
   if (args.npairs == 0) return cudaSuccess;
   const size_t smem = (size_t)CKQ * 32 * sizeof(uint2);
   switch (args.mode) {
-    case MODE_GENERAL: traceback_tiles_kernel<MODE_GENERAL><<<args.npairs, 32, smem, stream>>>(args); break;
-    case MODE_CMP: traceback_tiles_kernel<MODE_CMP><<<args.npairs, 32, smem, stream>>>(args); break;
-    case MODE_TAB: traceback_tiles_kernel<MODE_TAB><<<args.npairs, 32, smem, stream>>>(args); break;
+    case MODE_GENERAL: traceback_tiles_kernel<MODE_GENERAL, 0><<<args.npairs, 32, smem, stream>>>(args); break;
+    case MODE_CMP: traceback_tiles_kernel<MODE_CMP, 0><<<args.npairs, 32, smem, stream>>>(args); break;
+    case MODE_TAB:
+      if (args.addmode == 2)
+        traceback_tiles_kernel<MODE_TAB, 2><<<args.npairs, 32, smem, stream>>>(args);
+      else
+        traceback_tiles_kernel<MODE_TAB, 0><<<args.npairs, 32, smem, stream>>>(args);
+      break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

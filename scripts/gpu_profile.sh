@@ -10,7 +10,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches_$TAG.csv $LIST_CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "launch list rc=$?"
 $FULL_CMD > gpurun_out/plain_full_$TAG.json 2> gpurun_out/plain_full_$TAG.err &&
-ncu --set full --clock-control none --import-source on -k regex:fill_kernel -s 14 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:fill_kernel -s 2 -c 1 \
     -o gpurun_out/fill_$TAG $FULL_CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out | tail -12
+# full capture of the tile traceback kernel (same command, already run plain above)
+ncu --set full --clock-control none --import-source on -k regex:traceback_tiles -s 2 -c 1 \
+    -o gpurun_out/tbtiles_$TAG $FULL_CMD > gpurun_out/ncu_full_tb_$TAG.log 2>&1
+echo "tb capture rc=$?"
