@@ -267,7 +267,11 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     if (!std::strcmp(e, "tiles")) tiles_ = true;
     if (!std::strcmp(e, "dirs")) tiles_ = false;
   }
-  if (tiles_) variant_.R = 16;
+  if (tiles_) {
+    variant_.R = 32;  // measured best for the score-only fill (profiles/): 9.0 vs 7.9 TCUPS at R = 16
+    if (const char *e = std::getenv("SEQALK_FILL_R"))
+      if (std::atoi(e) == 16) variant_.R = 16;
+  }
   variant_.emit = !tiles_;
   const int R = variant_.R;
   int64_t maxlen = 1;
@@ -293,7 +297,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
       throw std::runtime_error("empty sequence: undefined in the reference (ceil(0/0) tile size, submit/xuliny-seqalkway.cpp:457)");
     maxlen = std::max<int64_t>(maxlen, std::max(m, n));
     const uint32_t ns = (uint32_t)num_strips(m, R);
-    const uint64_t brow_ints = tiles_ ? 2ull * ns * (4ull * (uint64_t)macro_cols(n) + 4)
+    const uint64_t brow_ints = tiles_ ? (uint64_t)(R / 8) * ns * (4ull * (uint64_t)macro_cols(n) + 4)
                                       : 4ull * (uint64_t)macro_cols(n) + 4;
     // directions, or (tile mode) the column checkpoints [nq / CKQ][rows padded to the strip]
     const uint64_t db = tiles_ ? (uint64_t)(macro_cols(n) / CKQ) * ns * (32ull * R) * 4 + 16
@@ -445,8 +449,18 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     uint64_t dir_off = 0, brow_off = 0, out_off = 0;
     uint32_t strip0 = 0;
     int max_strips = 0;
+    // inside a batch the pairs are laid out longest first (m + n): the traceback kernel's
+    // blocks and every level of the strip queue then start their longest work first, which
+    // shortens the tails; results still land at the task's slot
+    order_.resize(B.count);
+    for (size_t p = 0; p < B.count; ++p) order_[p] = (uint32_t)p;
+    std::stable_sort(order_.begin(), order_.end(), [&](uint32_t a, uint32_t c) {
+      const TaskIJ &ta = tasks_[B.first + a], &tc = tasks_[B.first + c];
+      return (int64_t)pack_->len[ta.i] + pack_->len[ta.j] > (int64_t)pack_->len[tc.i] + pack_->len[tc.j];
+    });
     for (size_t p = 0; p < B.count; ++p) {
-      const TaskIJ &tk = tasks_[B.first + p];
+      const size_t t_index = B.first + order_[p];
+      const TaskIJ &tk = tasks_[t_index];
       PairDesc d;
       d.x_off = pack_->off[tk.i];
       d.y_off = pack_->off[tk.j];
@@ -458,12 +472,12 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       d.strip0 = strip0;
       d.nstrips = num_strips(d.m, R);
       d.cap = (uint32_t)round_up((size_t)d.m + d.n, 16);
-      d.task_id = (int32_t)(B.first + p);
+      d.task_id = (int32_t)t_index;
       hp[p] = d;
-      hs[p] = result_slots_.empty() ? (uint32_t)(B.first + p) : result_slots_[B.first + p];
+      hs[p] = result_slots_.empty() ? (uint32_t)t_index : result_slots_[t_index];
       if (tiles_) {
         dir_off += round_up((uint64_t)(macro_cols(d.n) / CKQ) * d.nstrips * (32ull * R) * 4, 16);
-        brow_off += 2ull * d.nstrips * (4ull * (uint64_t)macro_cols(d.n) + 4);
+        brow_off += (uint64_t)(R / 8) * d.nstrips * (4ull * (uint64_t)macro_cols(d.n) + 4);
       } else {
         dir_off += (uint64_t)d.nstrips * strip_dir_bytes(d.n, R);
         brow_off += 4ull * (uint64_t)macro_cols(d.n) + 4;
@@ -658,7 +672,9 @@ bool DeviceWorker::fetch_alignment(size_t index_in_job, std::vector<uint8_t> &a1
   const Batch &B = batches_[b];
   if (index_in_job < B.first || index_in_job >= B.first + B.count) return false;
   Slot &S = slots_[b % nslots_];
-  const size_t p = index_in_job - B.first;
+  size_t p = 0;
+  while (p < S.last_pairs.size() && (size_t)S.last_pairs[p].task_id != index_in_job) ++p;
+  if (p == S.last_pairs.size()) return false;
   const PairDesc &d = S.last_pairs[p];
   PairAlign al;
   SEQALK_CUDA(cudaMemcpy(&al, static_cast<PairAlign *>(S.align.p) + p, sizeof al, cudaMemcpyDeviceToHost));

@@ -129,6 +129,7 @@ class DeviceWorker {
   SeqPack pack_copy_;
   std::vector<TaskIJ> tasks_;
   std::vector<uint32_t> result_slots_;
+  std::vector<uint32_t> order_;  // scratch: longest-first order of the current batch
   std::vector<Batch> batches_;
   int pxy_ = 0, pgap_ = 0;
   FillVariant variant_;

@@ -75,9 +75,9 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   const uint64_t bstride = EMIT ? 0 : (uint64_t)(4 * nq + 4);
   int32_t *bbase = a.brow + P.brow_off;
   const int4 *__restrict__ brow_rd =
-      reinterpret_cast<const int4 *>(EMIT ? bbase : bbase + (uint64_t)(first ? 0 : 2 * s - 1) * bstride);
+      reinterpret_cast<const int4 *>(EMIT ? bbase : bbase + (uint64_t)(first ? 0 : s * (R / 8) - 1) * bstride);
   int4 *__restrict__ brow_wr = reinterpret_cast<int4 *>(
-      EMIT ? bbase : bbase + (uint64_t)(2 * s + (lane == 31 ? 1 : 0)) * bstride);
+      EMIT ? bbase : bbase + (uint64_t)(s * (R / 8) + (lane * R) / TILE_ROWS) * bstride);  // kept row (DP row / 256) - 1
   uint4 *__restrict__ dout =
       reinterpret_cast<uint4 *>(a.dirs + P.dir_off + (uint64_t)s * ((uint64_t)ngroups * 512ull)) + lane;
   const unsigned *prev_progress = a.progress + P.strip0 + (first ? 0 : s - 1);
@@ -223,7 +223,13 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillArgs a) {
 typedef void (*FillKernelPtr)(const FillArgs);
 
 static FillKernelPtr pick_kernel(const FillVariant &v) {
-  if (!v.emit) {  // tile mode: R = 16 only
+  if (!v.emit && v.R == 32) {  // tile mode, 32 rows per lane
+    if (v.mode == MODE_GENERAL) return fill_kernel<32, MODE_GENERAL, 0, false>;
+    if (v.mode == MODE_CMP) return fill_kernel<32, MODE_CMP, 0, false>;
+    if (v.mode == MODE_TAB) return v.addmode == 2 ? fill_kernel<32, MODE_TAB, 2, false> : fill_kernel<32, MODE_TAB, 0, false>;
+    return nullptr;
+  }
+  if (!v.emit) {  // tile mode, 16 rows per lane
     if (v.R != 16) return nullptr;
     if (v.mode == MODE_GENERAL) return fill_kernel<16, MODE_GENERAL, 0, false>;
     if (v.mode == MODE_CMP) return v.addmode ? fill_kernel<16, MODE_CMP, 1, false> : fill_kernel<16, MODE_CMP, 0, false>;

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
   const int m = P.m, n = P.n;
   const int nq = (n + 3) >> 2;
   const uint64_t bstride = (uint64_t)(4 * nq + 4);
-  const uint64_t mpad = (uint64_t)P.nstrips * 512;  // the fill runs with 16 rows per lane
+  const uint64_t mpad = (uint64_t)P.nstrips * 32 * (uint64_t)a.R;  // rows padded to the fill's strips
   const int A = -2 * a.pgap, B = a.pxy - 2 * a.pgap;
 
   const uint8_t *__restrict__ xs = a.seq + P.x_off;  // raw characters for the output

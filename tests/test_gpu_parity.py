@@ -253,6 +253,9 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     {"SEQALK_TRACEBACK": "dirs"},
     {"SEQALK_TRACEBACK": "dirs", "SEQALK_FILL_ADD": "2"},
     {"SEQALK_TRACEBACK": "tiles", "SEQALK_FILL_ADD": "2"},
+    {"SEQALK_TRACEBACK": "tiles", "SEQALK_FILL_R": "16"},
+    {"SEQALK_TRACEBACK": "tiles", "SEQALK_FILL_R": "16", "SEQALK_FILL_TAB": "0"},
+    {"SEQALK_TRACEBACK": "tiles", "SEQALK_FILL_R": "16", "SEQALK_FORCE_GENERAL": "1"},
     {"SEQALK_TRACEBACK": "dirs", "SEQALK_FILL_R": "8", "SEQALK_FILL_TAB": "0"},
     {"SEQALK_TRACEBACK": "tiles"},
     {"SEQALK_TRACEBACK": "tiles", "SEQALK_FILL_TAB": "0"},
