@@ -258,6 +258,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   variant_.R = 16;  // measured best on B200 (profiles/): 16 rows per lane, cost table when possible
   variant_.addmode = 2;  // cost table lookup + add as one IDP.4A (FMA pipe) when the table applies
   if (const char *e = std::getenv("SEQALK_FILL_R")) variant_.R = std::atoi(e) == 8 ? 8 : 16;
+  if (const char *e = std::getenv("SEQALK_FILL_MINB")) variant_.minb = std::atoi(e);
   if (const char *e = std::getenv("SEQALK_FILL_ADD")) variant_.addmode = std::max(0, std::min(2, std::atoi(e)));
   // traceback mode: "tiles" = score-only fill + per-tile recompute (less work per cell, 8x
   // less memory), "dirs" = 2-bit directions for every cell in HBM.  auto: tiles unless the job

@@ -206,8 +206,9 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   }
 }
 
-template <int R, int MODE, int ADDMODE, bool EMIT>
-__global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillArgs a) {
+// MINB: minimum resident CTAs per SM the register allocation must allow (1 = no constraint)
+template <int R, int MODE, int ADDMODE, bool EMIT, int MINB = 1>
+__global__ void __launch_bounds__(FILL_THREADS, MINB) fill_kernel(const FillArgs a) {
   const int lane = threadIdx.x & 31;
   for (;;) {
     unsigned t = 0;
@@ -226,7 +227,12 @@ static FillKernelPtr pick_kernel(const FillVariant &v) {
   if (!v.emit && v.R == 32) {  // tile mode, 32 rows per lane
     if (v.mode == MODE_GENERAL) return fill_kernel<32, MODE_GENERAL, 0, false>;
     if (v.mode == MODE_CMP) return fill_kernel<32, MODE_CMP, 0, false>;
-    if (v.mode == MODE_TAB) return v.addmode == 2 ? fill_kernel<32, MODE_TAB, 2, false> : fill_kernel<32, MODE_TAB, 0, false>;
+    if (v.mode == MODE_TAB && v.addmode == 2) {
+      if (v.minb == 5) return fill_kernel<32, MODE_TAB, 2, false, 5>;
+      if (v.minb == 6) return fill_kernel<32, MODE_TAB, 2, false, 6>;
+      return fill_kernel<32, MODE_TAB, 2, false>;
+    }
+    if (v.mode == MODE_TAB) return fill_kernel<32, MODE_TAB, 0, false>;
     return nullptr;
   }
   if (!v.emit) {  // tile mode, 16 rows per lane

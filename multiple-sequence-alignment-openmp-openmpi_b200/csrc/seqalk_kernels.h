@@ -12,6 +12,7 @@ struct FillVariant {
   int R = 8;        // DP rows per lane (8 or 16); strip = 32*R rows
   int mode = MODE_CMP;
   int addmode = 0;  // 1: adds forced onto the FMA pipe (IMAD); 2: MODE_TAB lookup+add as one IDP.4A
+  int minb = 0;     // > 0: cap registers so that this many fill CTAs fit on an SM (tile mode, R = 32)
   bool emit = true; // true: directions mode (2-bit codes to HBM); false: tile mode (scores +
                     // checkpoints, directions recomputed by the traceback for the tiles it visits)
 };

@@ -19,11 +19,11 @@ namespace {
 constexpr int RT = 8;  // rows per lane in the recompute: 32 lanes x 8 rows = TILE_ROWS
 static_assert(32 * RT == TILE_ROWS, "tile height");
 
-// Right-to-left writer; every lane tracks the position, lane 0 stores.
+// Right-to-left writer (32-bit words); every lane tracks the position, lane 0 stores.
 struct BackWriter0 {
   uint8_t *base;
   uint32_t pos;
-  uint64_t acc;
+  uint32_t acc;
   bool store;
   __device__ __forceinline__ void init(uint8_t *b, uint32_t end, bool st) {
     base = b;
@@ -31,16 +31,16 @@ struct BackWriter0 {
     acc = 0;
     store = st;
   }
-  __device__ __forceinline__ void put(uint8_t ch) {
+  __device__ __forceinline__ void put(uint32_t ch) {
     --pos;
-    acc |= (uint64_t)ch << (8 * (pos & 7));
-    if ((pos & 7) == 0) {
-      if (store) *reinterpret_cast<uint64_t *>(base + pos) = acc;
+    acc |= ch << (8 * (pos & 3));
+    if ((pos & 3) == 0) {
+      if (store) *reinterpret_cast<uint32_t *>(base + pos) = acc;
       acc = 0;
     }
   }
   __device__ __forceinline__ void finish() {
-    if ((pos & 7) && store) *reinterpret_cast<uint64_t *>(base + (pos & ~7u)) = acc;
+    if ((pos & 3) && store) *reinterpret_cast<uint32_t *>(base + (pos & ~3u)) = acc;
   }
 };
 
@@ -49,6 +49,11 @@ struct BackWriter0 {
 template <int MODE, int ADDMODE>
 __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs a) {
   extern __shared__ uint2 sdirs[];  // [CKQ][32]: codes of the tile's macro column qc, lane t
+  // the tile's characters, staged once per tile for the walk: x rows, then y columns
+  uint64_t *schars = reinterpret_cast<uint64_t *>(sdirs + CKQ * 32);
+  const uint8_t *sxb = reinterpret_cast<const uint8_t *>(schars);
+  const uint8_t *syb = sxb + TILE_ROWS;
+  const uint32_t *sdirs32 = reinterpret_cast<const uint32_t *>(sdirs);
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x;
   const uint32_t p = blockIdx.x;
@@ -72,7 +77,7 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
   w2.init(a.out + P.out_off + P.cap, (uint32_t)(m + n), lane == 0);
 
   int i = m, j = n;
-  long long cost = 0;
+  int cost = 0;
   while (i > 0 && j > 0) {
     // ---- the tile containing (i, j), cut to the rows <= i and columns <= j
     const int hs = (i - 1) / TILE_ROWS, cb = (j - 1) / (4 * CKQ);
@@ -97,6 +102,11 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
 #pragma unroll
         for (int r = 0; r < RT; ++r) h[r] = 0;
       }
+    }
+    {  // stage the tile's characters (8 per lane; rows / columns past the ends are never walked)
+      const int r0 = row0 + lane * 8, c0 = col0 + lane * 8;
+      schars[lane] = r0 < m ? *reinterpret_cast<const uint64_t *>(xs + r0) : 0ull;
+      schars[32 + lane] = c0 < n ? *reinterpret_cast<const uint64_t *>(ys + c0) : 0ull;
     }
     const int32_t *toprow = hs > 0 ? brow + (uint64_t)(hs - 1) * bstride : nullptr;
     int dg = __shfl_up_sync(FULL, h[RT - 1], 1);
@@ -136,35 +146,36 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
     }
     __syncwarp();
     // ---- walk inside the tile (every lane walks; lane 0 writes)
-    while (i - 1 >= row0 && j - 1 >= col0) {
-      const int li = i - 1 - row0, lj = j - 1 - col0;
-      const int t = li / RT, r = li % RT, qc = lj >> 2, c = lj & 3;
-      const int idx = c * RT + r;
-      const uint2 wv = sdirs[qc * 32 + t];
-      const uint32_t word = (idx / CELLS_PER_WORD) ? wv.y : wv.x;
-      const uint32_t code = (word >> (30 - 2 * (idx % CELLS_PER_WORD))) & 3u;
-      const uint8_t xch = xs[i - 1], ych = ys[j - 1];
+    int li = i - 1 - row0, lj = j - 1 - col0;
+    while (li >= 0 && lj >= 0) {
+      const unsigned t = (unsigned)li >> 3, r = (unsigned)li & 7u, qc = (unsigned)lj >> 2, c = (unsigned)lj & 3u;
+      const unsigned idx = c * RT + r;
+      const uint32_t word = sdirs32[(qc * 32 + t) * 2 + (idx >> 4)];
+      const uint32_t code = (word >> (30 - 2 * (idx & 15u))) & 3u;
+      const uint32_t xch = sxb[li], ych = syb[lj];
       if (!(code & DIR_NOT_DIAG)) {
         w1.put(xch);
         w2.put(ych);
         cost += (xch == ych) ? 0 : a.pxy;
-        --i;
-        --j;
+        --li;
+        --lj;
       } else if (!(code & DIR_LEFT_BETTER)) {
         w1.put(xch);
         w2.put('_');
         cost += a.pgap;
-        --i;
+        --li;
       } else {
         w1.put('_');
         w2.put(ych);
         cost += a.pgap;
-        --j;
+        --lj;
       }
     }
+    i = row0 + li + 1;
+    j = col0 + lj + 1;
     __syncwarp();
   }
-  cost += (long long)(i + j) * a.pgap;
+  cost += (i + j) * a.pgap;
   for (; i > 0; --i) {
     w1.put(xs[i - 1]);
     w2.put('_');
@@ -181,13 +192,13 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
     res.start = start;
     res.len = (uint32_t)(m + n) - start;
     a.align[p] = res;
-    a.path_cost[p] = (int32_t)cost;
+    a.path_cost[p] = cost;
   }
 }
 
 cudaError_t launch_traceback_tiles(const TracebackArgs &args, cudaStream_t stream) {
   if (args.npairs == 0) return cudaSuccess;
-  const size_t smem = (size_t)CKQ * 32 * sizeof(uint2);
+  const size_t smem = (size_t)CKQ * 32 * sizeof(uint2) + 2 * TILE_ROWS;
   switch (args.mode) {
     case MODE_GENERAL: traceback_tiles_kernel<MODE_GENERAL, 0><<<args.npairs, 32, smem, stream>>>(args); break;
     case MODE_CMP: traceback_tiles_kernel<MODE_CMP, 0><<<args.npairs, 32, smem, stream>>>(args); break;
