@@ -268,6 +268,14 @@ def main():
     barrier()
 
     if rank == 0:
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this
+        # workload (profiles/traffic.json), per launch; null when no capture exists for it
+        ncu_traffic = {}
+        try:
+            allt = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ncu_traffic = allt.get(f"{args.workload}:{'tiles' if tile_mode else 'dirs'}", {})
+        except (OSError, ValueError):
+            pass
         ms = statistics.mean(step_s) * 1e3
         value = cells / (ms * 1e-3) / 1e9
         e2e_ms = statistics.mean(e2e_s) * 1e3
@@ -288,7 +296,8 @@ def main():
             "gpu_launches": total_launches,
             "roofline": {
                 "bound": "int_alu", "achieved": agg_ops_rate / world / 1e9, "peak": peak / 1e9, "unit": "Gop/s",
-                "frac": (agg_ops_rate / world) / peak if peak else None, "traffic": None,
+                "frac": (agg_ops_rate / world) / peak if peak else None,
+                "traffic": ncu_traffic.get("dram_bytes_per_launch"), "traffic_source": ncu_traffic.get("source"),
                 "per": "GPU (mean over ranks)", "ops_per_cell": OPS_PER_CELL,
                 "peak_source": "measured live: dependent-free LOP3 issue rate (seqalk_measure_int_peaks), ALU pipe",
                 "peak_nominal_at_sm_mhz": 148 * 64 * sm_mhz * 1e6 / 1e9 if sm_mhz else None,
@@ -298,7 +307,8 @@ def main():
                 "hbm": {"bound": "hbm", "achieved": agg_dir_rate / world / 1e9, "unit": "GB/s",
                         "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
-                        "note": "algorithmic bytes = 0.25 B/cell of packed directions written by the fill"},
+                        "note": "algorithmic bytes written by the fill: 0.25 B/cell of packed directions (dirs mode) "
+                                "or the kept rows + column checkpoints (tiles mode)"},
             },
             "kernel_ms_per_step": {"fill": fill_ms / args.steps, "traceback": tb_ms / args.steps,
                                    "digest": dg_ms / args.steps, "note": "rank 0, CUDA events on the launching streams"},

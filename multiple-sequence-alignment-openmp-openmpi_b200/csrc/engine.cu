@@ -316,7 +316,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     cur.out_bytes += 2ull * round_up((size_t)m + n, 16);
     cur.nstrips += ns;
     stats_.cells += (uint64_t)m * (uint64_t)n;
-    stats_.dir_bytes += db;
+    stats_.dir_bytes += bb;
   }
   if (cur.count) batches_.push_back(cur);
   while (next_end < ends.size()) {
