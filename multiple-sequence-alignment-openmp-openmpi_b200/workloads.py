@@ -48,8 +48,18 @@ def mixed(k: int, seed: int, lo: int = 1000, hi: int = 20000) -> List[bytes]:
     return _bases(seed, k, [int(v) for v in lens])
 
 
+def _golden(name: str):
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return parse_input(open(os.path.join(root, "tests", "golden", name), "rb").read())
+
+
 # name -> (description, factory)
 CONFIGS = {
+    "cfg1": ("mseq1.dat (reference fixture, k=9)", lambda: _golden("mseq1.dat")),
+    "cfg2": ("mseq-big13-example.txt (reference fixture, k=13, 30k-90k, 278.5 G cells)",
+             lambda: _golden("mseq-big13-example.txt")),
     "cfg3": ("synthetic k=200, length 10k uniform ACGT, all-pairs (seed 200)", lambda: (3, 2, uniform(200, 10000, 200))),
     "cfg4": ("synthetic k=1000, lengths 1k-20k mixed, all-pairs (seed 1000)", lambda: (3, 2, mixed(1000, 1000))),
     "cfg5": ("synthetic k=2, length 200k single pair (seed 2)", lambda: (3, 2, uniform(2, 200000, 2))),

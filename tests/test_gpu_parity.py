@@ -335,3 +335,36 @@ def test_traceback_modes_on_long_and_skewed_pairs(seqalk, oracle, workloads, mon
     pen1, xans, yans = seqalk.get_minimum_penalty(x, y, 3, 2)
     open_, a1, a2, _ = oracle.pair(x, y, 3, 2)
     assert pen1 == open_ and seqalk.alignment_strings(xans, yans) == (a1, a2)
+
+
+def test_cfg4_random_task_sample_vs_oracle(seqalk, oracle, workloads):
+    """Config 4 at full shape: 48 seeded task ids out of the 499 500 (plus the largest and the
+    most skewed pair), run as a job on the full k=1000 input, each checked against the oracle's
+    penalty and problemhash.  (The full digest is checked for equality across traceback modes
+    and GPU counts by bench.py / profiles; the CPU cannot do 5.5e13 cells.)"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    genes = workloads.mixed(1000, 1000)
+    lens = np.array([len(g) for g in genes])
+    rnd = random.Random(4)
+    T = seqalk.num_tasks(1000)
+    ids = sorted(set(rnd.randrange(T) for _ in range(48)))
+    big = np.argsort(lens)[-2:]
+    i, j = int(max(big)), int(min(big))
+    ids.append(i * (i - 1) // 2 + j)                      # largest pair
+    lo, hi = int(np.argmin(lens)), int(np.argmax(lens))
+    i, j = max(lo, hi), min(lo, hi)
+    ids.append(i * (i - 1) // 2 + j)                      # most skewed pair
+    ids = np.array(sorted(set(ids)), dtype=np.int64)
+    with seqalk.Job(genes, 3, 2, ids) as job:
+        job.run()
+        pen, dig = job.fetch()
+
+    def check(k):
+        i, j = seqalk.task_ij(int(ids[k]))
+        p, _, _, h = oracle.pair(genes[i], genes[j], 3, 2)
+        return p == pen[k] and h == dig[k].tobytes().hex()
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        ok = list(ex.map(check, range(len(ids))))
+    assert all(ok), [int(ids[k]) for k, v in enumerate(ok) if not v]
