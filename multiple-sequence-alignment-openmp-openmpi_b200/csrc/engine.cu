@@ -261,9 +261,9 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   if (const char *e = std::getenv("SEQALK_FILL_MINB")) variant_.minb = std::atoi(e);
   if (const char *e = std::getenv("SEQALK_FILL_ADD")) variant_.addmode = std::max(0, std::min(2, std::atoi(e)));
   // traceback mode: "tiles" = score-only fill + per-tile recompute (less work per cell, 8x
-  // less memory), "dirs" = 2-bit directions for every cell in HBM.  auto: tiles unless the job
-  // is a handful of pairs (a lone long pair walks its tiles serially on one warp).
-  tiles_ = tasks_.size() >= 8;
+  // less memory; measured faster on every BASELINE config, profiles/), "dirs" = 2-bit
+  // directions for every cell in HBM (SEQALK_TRACEBACK=dirs).
+  tiles_ = true;
   if (const char *e = std::getenv("SEQALK_TRACEBACK")) {
     if (!std::strcmp(e, "tiles")) tiles_ = true;
     if (!std::strcmp(e, "dirs")) tiles_ = false;
@@ -274,6 +274,14 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
       if (std::atoi(e) == 16) variant_.R = 16;
   }
   variant_.emit = !tiles_;
+  {
+    // few long pairs: the GPU is filled by the strips of the same pair running as a wavefront,
+    // so use thinner strips (more of them) and publish progress more often
+    uint64_t strips = 0;
+    for (const TaskIJ &tk : tasks_) strips += (uint64_t)num_strips(std::max(pack_->len[tk.i], 1), variant_.R);
+    few_pairs_ = strips < 2ull * (uint64_t)sm_count_ * 16;
+    if (few_pairs_ && tiles_ && !std::getenv("SEQALK_FILL_R")) variant_.R = 16;
+  }
   const int R = variant_.R;
   int64_t maxlen = 1;
   Batch cur{0, 0, 0, 0, 0, 0, 0};
@@ -513,6 +521,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.seq = static_cast<const uint8_t *>(seq_.p);
     fa.codes = static_cast<const uint8_t *>(codes_.p);
     fa.one = 1;
+    fa.publish_shift = few_pairs_ ? PUBLISH_SHIFT_FEW : PUBLISH_SHIFT_MANY;
     fa.pairs = static_cast<const PairDesc *>(S.pairs.p);
     fa.tasks = static_cast<const StripTask *>(S.tasks.p);
     fa.ntasks = B.nstrips;

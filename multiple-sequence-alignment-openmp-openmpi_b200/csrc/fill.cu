@@ -198,7 +198,7 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
       const int done = min(nq, (g + 1) * G - 31);
       if (done > 0) {
         const int prev_done = max(0, min(nq, g * G - 31));
-        if (done != prev_done && (done == nq || (done / PUBLISH_EVERY) != (prev_done / PUBLISH_EVERY))) {
+        if (done != prev_done && (done == nq || (done >> a.publish_shift) != (prev_done >> a.publish_shift))) {
           if (lane == 31) st_release_u32(my_progress, (unsigned)done);
         }
       }

@@ -19,8 +19,10 @@ struct FillVariant {
 // tile mode: a column checkpoint every CKQ macro columns (4*CKQ DP columns), a row every 256 rows
 constexpr int CKQ = 64;
 constexpr int TILE_ROWS = 256;
-// bottom-row progress is published every PUBLISH_EVERY macro columns (and at strip end)
-constexpr int PUBLISH_EVERY = 64;
+// bottom-row progress is published every 2^publish_shift macro columns (and at strip end):
+// 64 when a batch has plenty of independent pairs, 16 when consecutive strips of a few long
+// pairs must run as a tight wavefront (shorter start-up ramp)
+constexpr int PUBLISH_SHIFT_MANY = 6, PUBLISH_SHIFT_FEW = 4;
 constexpr int TRACEBACK_THREADS = 32;
 constexpr int DIGEST_THREADS = 64;
 // bytes that may be read past the end of the packed sequence / alignment buffers
@@ -38,6 +40,7 @@ struct FillArgs {
   uint8_t *dirs;            // packed 2-bit directions
   int32_t pxy, pgap;
   int32_t one;              // == 1, opaque to the compiler (see add_i in fill.cu)
+  int32_t publish_shift;    // log2 of the publication interval in macro columns
 };
 
 struct TracebackArgs {

@@ -230,7 +230,14 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     reported penalty, the device digest equals hashlib over the returned strings, the score is
     symmetric, and a 20 000-column prefix problem matches the oracle's linear-memory score."""
     x, y = workloads.uniform(2, 200000, 2)[::-1]  # task (1,0): x = genes[1], y = genes[0]
+    # the 10 GB packed-direction path (dirs mode) and the default tile mode must agree
+    os.environ["SEQALK_TRACEBACK"] = "dirs"
+    try:
+        pen_d, xans_d, yans_d = seqalk.get_minimum_penalty(x, y, 3, 2)
+    finally:
+        os.environ.pop("SEQALK_TRACEBACK", None)
     pen, xans, yans = seqalk.get_minimum_penalty(x, y, 3, 2)
+    assert pen_d == pen and np.array_equal(xans_d, xans) and np.array_equal(yans_d, yans)
     ph = _alignment_properties(x, y, pen, xans, yans, 3, 2, seqalk)
     digest, pens = seqalk.get_minimum_penalties([y, x], 3, 2)
     assert pens[0] == pen
