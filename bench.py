@@ -178,7 +178,8 @@ def main():
     lens = [len(g) for g in genes]
     cells = workloads.total_cells(genes)
     T = len(genes) * (len(genes) - 1) // 2
-    nchunks = args.nchunks or (8 if (world > 1 and T >= 4096) else 1)
+    # chunks of task ids: rank 0 folds the hash chain of chunk c while the GPUs work on chunk c+1
+    nchunks = args.nchunks or (8 if T >= 4096 else 1)
 
     def barrier():
         torch.cuda.synchronize()

@@ -76,6 +76,12 @@ int seqalk_partition(const int32_t *lens, int32_t k, int64_t id_begin, int64_t i
 int seqalk_partition_all(const int32_t *lens, int32_t k, int64_t id_begin, int64_t id_end, int32_t nranks,
                          int64_t *ids_out, int64_t *counts_out);
 
+/* The shards of `nchunks` consecutive id ranges (chunk c = ids [T*c/nchunks, T*(c+1)/nchunks))
+ * for every rank, computed in parallel: ids_out (capacity T) = chunk 0 rank 0, chunk 0 rank 1,
+ * ..., chunk 1 rank 0, ...; counts_out[nchunks*nranks] in the same order. */
+int seqalk_partition_chunks(const int32_t *lens, int32_t k, int32_t nranks, int32_t nchunks, int64_t *ids_out,
+                            int64_t *counts_out);
+
 typedef struct seqalk_job seqalk_job_t;
 
 typedef struct seqalk_stats {

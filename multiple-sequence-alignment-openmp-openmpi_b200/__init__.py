@@ -27,7 +27,7 @@ import numpy as np
 
 __all__ = [
     "SeqalkError", "lib", "library_path", "getMinimumPenalties", "getMinimumPenalty", "do_MPI_task",
-    "get_minimum_penalties", "get_minimum_penalty", "Job", "JobStats", "partition", "partition_all", "task_ij",
+    "get_minimum_penalties", "get_minimum_penalty", "Job", "JobStats", "partition", "partition_all", "partition_chunks", "task_ij",
     "num_tasks", "fold_chain", "sha512_hex", "init", "shutdown", "device_count", "version",
 ]
 
@@ -71,6 +71,7 @@ C_ABI = [
     ("seqalk_task_ij", _c.c_int, [_c.c_int64, _I32P, _I32P]),
     ("seqalk_partition", _c.c_int, [_I32P, _c.c_int32, _c.c_int64, _c.c_int64, _c.c_int32, _c.c_int32, _I64P, _I64P]),
     ("seqalk_partition_all", _c.c_int, [_I32P, _c.c_int32, _c.c_int64, _c.c_int64, _c.c_int32, _I64P, _I64P]),
+    ("seqalk_partition_chunks", _c.c_int, [_I32P, _c.c_int32, _c.c_int32, _c.c_int32, _I64P, _I64P]),
     ("seqalk_job_create", _c.c_int, [_c.c_int32, _c.POINTER(_c.c_void_p), _I32P, _c.c_int32, _c.c_int32, _c.c_int32, _I64P, _c.c_int64, _c.POINTER(_c.c_void_p)]),
     ("seqalk_job_run", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
     ("seqalk_job_set_chunks", _c.c_int, [_c.c_void_p, _I64P, _c.c_int32]),
@@ -272,6 +273,20 @@ def partition_all(lens: Iterable[int], nranks: int, id_begin: int = 0,
                                       out.ctypes.data_as(_I64P), counts.ctypes.data_as(_I64P)))
     ends = np.cumsum(counts)
     return [out[e - c:e].copy() for c, e in zip(counts, ends)]
+
+
+def partition_chunks(lens: Iterable[int], nranks: int, nchunks: int) -> List[List[np.ndarray]]:
+    """LPT shards of ``nchunks`` consecutive id ranges for every rank: result[c][r] (ids increasing)."""
+    lens_a = np.ascontiguousarray(np.asarray(list(lens), dtype=np.int32))
+    k = len(lens_a)
+    T = k * (k - 1) // 2
+    out = np.zeros(max(T, 1), dtype=np.int64)
+    counts = np.zeros(nchunks * nranks, dtype=np.int64)
+    _check(lib().seqalk_partition_chunks(lens_a.ctypes.data_as(_I32P), k, int(nranks), int(nchunks),
+                                         out.ctypes.data_as(_I64P), counts.ctypes.data_as(_I64P)))
+    ends = np.cumsum(counts)
+    flat = [out[e - c:e] for c, e in zip(counts, ends)]
+    return [flat[c * nranks:(c + 1) * nranks] for c in range(nchunks)]
 
 
 class JobStats(dict):

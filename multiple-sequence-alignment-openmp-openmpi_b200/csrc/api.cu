@@ -373,6 +373,37 @@ int seqalk_partition_all(const int32_t *lens, int32_t k, int64_t id_begin, int64
   }
 }
 
+int seqalk_partition_chunks(const int32_t *lens, int32_t k, int32_t nranks, int32_t nchunks, int64_t *ids_out,
+                            int64_t *counts_out) {
+  try {
+    if (!lens || !ids_out || !counts_out || nranks < 1 || nchunks < 1) return fail("bad argument");
+    const int64_t T = seqalk_num_tasks(k);
+    std::vector<std::vector<std::vector<int64_t>>> per(nchunks);
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(nchunks);
+    for (int c = 0; c < nchunks; ++c)
+      th.emplace_back([&, c]() {
+        try {
+          partition_lpt(lens, k, T * c / nchunks, T * (c + 1) / nchunks, nranks, per[c]);
+        } catch (const std::exception &e) {
+          errs[c] = e.what();
+        }
+      });
+    for (std::thread &t : th) t.join();
+    for (const std::string &e : errs)
+      if (!e.empty()) return fail(e.c_str());
+    int64_t *w = ids_out;
+    for (int c = 0; c < nchunks; ++c)
+      for (int r = 0; r < nranks; ++r) {
+        counts_out[(size_t)c * nranks + r] = (int64_t)per[c][r].size();
+        w = std::copy(per[c][r].begin(), per[c][r].end(), w);
+      }
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
 int seqalk_job_create(int32_t device, const char *const *seqs, const int32_t *lens, int32_t k, int32_t pxy,
                       int32_t pgap, const int64_t *task_ids, int64_t ntasks, seqalk_job_t **job_out) {
   try {

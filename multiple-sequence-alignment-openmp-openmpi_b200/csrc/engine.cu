@@ -37,26 +37,45 @@ void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
   }
   bytes.assign(total + BUFFER_SLACK, 0);
   for (int i = 0; i < k; ++i) std::memcpy(bytes.data() + off[i], seqs[i], (size_t)lens[i]);
-  // alphabet: with <= 4 distinct letters (DNA) the fill can use a per-row cost table
-  bool seen[256] = {false};
-  int nletters = 0;
-  uint8_t code_of[256] = {0};
-  for (int i = 0; i < k && nletters <= 4; ++i)
-    for (int32_t c = 0; c < lens[i]; ++c) {
-      const uint8_t ch = (uint8_t)seqs[i][c];
-      if (!seen[ch]) {
-        seen[ch] = true;
-        if (nletters < 4) code_of[ch] = (uint8_t)(8 * nletters);  // stored as the byte's bit offset
-        if (++nletters > 4) break;
-      }
+  // alphabet: with <= 4 distinct letters (DNA) the fill can use a per-row cost table; the
+  // letters are remapped on the GPU (remap_letters) from this 256-entry table
+  uint8_t seen[256] = {0};
+  for (int i = 0; i < k; ++i) {
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(seqs[i]);
+    for (int32_t c = 0; c < lens[i]; ++c) seen[p[c]] = 1;  // branch-free pass over the input
+  }
+  nletters = 0;
+  std::memset(code_of, 0, sizeof code_of);
+  for (int ch = 0; ch < 256; ++ch)
+    if (seen[ch]) {
+      if (nletters < 4) code_of[ch] = (uint8_t)(8 * nletters);  // stored as the byte's bit offset
+      ++nletters;
     }
-  codes.clear();
-  if (nletters <= 4) {
-    codes.assign(bytes.size(), 0);
-    for (int i = 0; i < k; ++i)
-      for (int32_t c = 0; c < lens[i]; ++c) codes[off[i] + c] = code_of[(uint8_t)seqs[i][c]];
+}
+
+namespace {
+struct Lut256 {
+  uint8_t v[256];
+};
+__global__ void remap_letters_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n16,
+                                     const Lut256 lut) {
+  // 16 bytes per thread per iteration; padding bytes (0) map to code_of[0] like any letter
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 v = s4[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t o = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) o |= (uint32_t)lut.v[(w[k] >> (8 * b)) & 0xffu] << (8 * b);
+      w[k] = o;
+    }
+    d4[i] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+}  // namespace
 
 uint64_t total_cells(const SeqPack &pack, const std::vector<TaskIJ> &tasks) {
   uint64_t c = 0;
@@ -82,39 +101,28 @@ void task_from_id(int64_t id, int32_t *i, int32_t *j) {
 
 void partition_lpt(const int32_t *lens, int k, int64_t id_begin, int64_t id_end, int nranks,
                    std::vector<std::vector<int64_t>> &per_rank) {
+  // Greedy list scheduling in id order: every task goes to the rank with the fewest cells so
+  // far (ties: lowest rank).  The imbalance is bounded by one task (<= 4e8 cells of ~1e12 per
+  // rank and chunk at k = 1000, i.e. < 0.05 %), each rank's ids come out increasing without a
+  // sort, and the whole k = 1000 plan costs a few milliseconds.
   (void)k;
   per_rank.assign(nranks, {});
   if (id_end <= id_begin) return;
-  struct Item {
-    uint64_t cells;
-    int64_t id;
-  };
-  std::vector<Item> items;
-  items.reserve((size_t)(id_end - id_begin));
+  for (int r = 0; r < nranks; ++r) per_rank[r].reserve((size_t)((id_end - id_begin) / nranks + 16));
+  std::vector<uint64_t> load((size_t)nranks, 0);
   int32_t i, j;
   task_from_id(id_begin, &i, &j);
   for (int64_t id = id_begin; id < id_end; ++id) {
-    items.push_back(Item{(uint64_t)lens[i] * (uint64_t)lens[j], id});
+    int best = 0;
+    for (int r = 1; r < nranks; ++r)
+      if (load[r] < load[best]) best = r;
+    load[best] += (uint64_t)lens[i] * (uint64_t)lens[j];
+    per_rank[best].push_back(id);
     if (++j == i) {
       ++i;
       j = 0;
     }
   }
-  std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-    return a.cells != b.cells ? a.cells > b.cells : a.id < b.id;
-  });
-  // min-heap of (load, rank)
-  typedef std::pair<uint64_t, int> LR;
-  std::priority_queue<LR, std::vector<LR>, std::greater<LR>> heap;
-  for (int r = 0; r < nranks; ++r) heap.push(LR(0, r));
-  for (const Item &it : items) {
-    LR top = heap.top();
-    heap.pop();
-    per_rank[top.second].push_back(it.id);
-    top.first += it.cells;
-    heap.push(top);
-  }
-  for (int r = 0; r < nranks; ++r) std::sort(per_rank[r].begin(), per_rank[r].end());
 }
 
 // ------------------------------------------------------------------ DeviceWorker
@@ -213,15 +221,23 @@ void DeviceWorker::ensure_stage(Slot &s, size_t bytes) {
 
 void DeviceWorker::load(const SeqPack &pack) {
   SEQALK_CUDA(cudaSetDevice(dev_));
-  pack_copy_ = pack;  // lengths/offsets are needed for planning; bytes are small (<= MBs)
+  // lengths/offsets are needed for planning; the bytes stay with the caller
+  pack_copy_.k = pack.k;
+  pack_copy_.off = pack.off;
+  pack_copy_.len = pack.len;
+  pack_copy_.nletters = pack.nletters;
   pack_ = &pack_copy_;
-  ensure(seq_, pack.bytes.size());
+  ensure(seq_, (pack.bytes.size() + 15) / 16 * 16);  // the letter remap reads whole 16 B words
   SEQALK_CUDA(cudaMemcpyAsync(seq_.p, pack.bytes.data(), pack.bytes.size(), cudaMemcpyHostToDevice,
                               fill_stream_));
-  if (!pack.codes.empty()) {
-    ensure(codes_, pack.codes.size());
-    SEQALK_CUDA(cudaMemcpyAsync(codes_.p, pack.codes.data(), pack.codes.size(), cudaMemcpyHostToDevice,
-                                fill_stream_));
+  if (pack.nletters <= 4) {
+    const size_t n16 = (pack.bytes.size() + 15) / 16;
+    ensure(codes_, n16 * 16);
+    Lut256 lut;
+    std::memcpy(lut.v, pack.code_of, 256);
+    remap_letters_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 4096), 256, 0, fill_stream_>>>(
+        static_cast<const uint8_t *>(seq_.p), static_cast<uint8_t *>(codes_.p), n16, lut);
+    SEQALK_CUDA(cudaGetLastError());
   }
   SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
 }
@@ -339,7 +355,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   if (const char *e = std::getenv("SEQALK_FORCE_GENERAL"))
     if (std::atoi(e)) general = true;
   // cost table (PRMT) needs <= 4 letters and both shifted costs in a signed byte
-  bool table = !pack_->codes.empty() && 2 * (int64_t)pgap <= 127 && (int64_t)pxy - 2 * (int64_t)pgap <= 127 &&
+  bool table = pack_->nletters <= 4 && 2 * (int64_t)pgap <= 127 && (int64_t)pxy - 2 * (int64_t)pgap <= 127 &&
                (int64_t)pxy - 2 * (int64_t)pgap >= -128;
   if (const char *e = std::getenv("SEQALK_FILL_TAB"))
     if (!std::atoi(e)) table = false;

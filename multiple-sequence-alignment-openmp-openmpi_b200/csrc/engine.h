@@ -25,7 +25,8 @@ struct SeqPack {
   std::vector<uint8_t> bytes;
   std::vector<uint32_t> off;
   std::vector<int32_t> len;
-  std::vector<uint8_t> codes;  // same layout as bytes, letters remapped to 8*(0..3); empty if > 4 letters
+  int nletters = 256;          // distinct byte values in the input
+  uint8_t code_of[256];        // <= 4 letters: letter -> 8*(0..3) (bit offset of its cost-table byte)
   int k = 0;
   void build(const char *const *seqs, const int32_t *lens, int k);
 };
@@ -161,8 +162,8 @@ void all_tasks(int k, std::vector<TaskIJ> &out);
 inline int64_t task_id_of(int i, int j) { return (int64_t)i * (i - 1) / 2 + j; }
 void task_from_id(int64_t id, int32_t *i, int32_t *j);
 
-// Cell-balanced shard of tasks [id_begin, id_end) over nranks (LPT: largest first onto
-// the least loaded rank, ties by rank index), each rank's list returned in id order.
+// Cell-balanced shard of tasks [id_begin, id_end) over nranks (greedy list scheduling in id
+// order onto the least loaded rank, ties by rank index), each rank's list in id order.
 void partition_lpt(const int32_t *lens, int k, int64_t id_begin, int64_t id_end, int nranks,
                    std::vector<std::vector<int64_t>> &per_rank);
 

@@ -22,7 +22,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import Job, fold_chain, partition_all
+from . import Job, fold_chain, partition_chunks
 
 ComputeFn = Callable[[Sequence[bytes], int, int, np.ndarray], Tuple[np.ndarray, np.ndarray]]
 
@@ -36,8 +36,7 @@ class ShardPlan:
         nchunks = max(1, min(nchunks, max(T, 1)))
         self.T, self.world = T, world
         self.bounds = [T * c // nchunks for c in range(nchunks + 1)]
-        self.ids: List[List[np.ndarray]] = [
-            partition_all(lens, world, self.bounds[c], self.bounds[c + 1]) for c in range(nchunks)]
+        self.ids: List[List[np.ndarray]] = partition_chunks(lens, world, nchunks)  # one parallel LPT pass
 
     @property
     def nchunks(self) -> int:
