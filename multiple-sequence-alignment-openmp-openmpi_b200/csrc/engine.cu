@@ -145,7 +145,6 @@ DeviceWorker::DeviceWorker(int device) : dev_(device) {
     SEQALK_CUDA(cudaEventCreateWithFlags(&s.fill_done, cudaEventDisableTiming));
     SEQALK_CUDA(cudaEventCreateWithFlags(&s.post_done, cudaEventDisableTiming));
   }
-  ensure(err_, sizeof(uint32_t));
 }
 
 int DeviceWorker::slots_from_env() {
@@ -166,8 +165,8 @@ DeviceWorker::~DeviceWorker() {
   for (cudaEvent_t e : chunk_ev_) cudaEventDestroy(e);
   cudaDeviceSynchronize();
   for (Slot &s : slots_) {
-    for (DevBuf *b : {&s.pairs, &s.tasks, &s.slots, &s.progress, &s.brow, &s.dirs, &s.out, &s.align, &s.pen,
-                      &s.cost, &s.counter})
+    for (DevBuf *b : {&s.pairs, &s.tasks, &s.slots, &s.progress, &s.brow, &s.dirs, &s.out, &s.align, &s.cost,
+                      &s.counter})
       release(*b);
     if (s.h_stage) cudaFreeHost(s.h_stage);
     if (s.staged) cudaEventDestroy(s.staged);
@@ -180,7 +179,6 @@ DeviceWorker::~DeviceWorker() {
   release(codes_);
   release(res_pen_);
   release(res_dig_);
-  release(err_);
   if (h_res_) cudaFreeHost(h_res_);
   for (cudaEvent_t e : ev_) cudaEventDestroy(e);
 }

@@ -108,7 +108,7 @@ class DeviceWorker {
     cudaEvent_t fill_done = nullptr;   // fill of the batch using this slot finished
     cudaEvent_t post_done = nullptr;   // traceback + digest (+ D2H) of that batch finished
     bool post_pending = false;
-    DevBuf pairs, tasks, slots, progress, brow, dirs, out, align, pen, cost, counter;
+    DevBuf pairs, tasks, slots, progress, brow, dirs, out, align, cost, counter;
     void *h_stage = nullptr;  // pinned staging: pairs | tasks | slots
     size_t h_cap = 0;
     cudaEvent_t staged = nullptr;  // H2D of the staging buffer finished
@@ -137,7 +137,7 @@ class DeviceWorker {
   bool few_pairs_ = false;  // fewer strips than ~2x the resident warps: wavefront-bound job
   bool tiles_ = false;  // tile mode: score-only fill + checkpoints, directions recomputed per tile
   Batch need_{0, 0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches
-  DevBuf res_pen_, res_dig_, err_;
+  DevBuf res_pen_, res_dig_;
   void run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties, char *fold_hex,
                 size_t batch_begin, size_t batch_end);
   std::vector<size_t> chunk_batch_;  // chunk c = batches [chunk_batch_[c], chunk_batch_[c+1])

@@ -375,3 +375,30 @@ def test_cfg4_random_task_sample_vs_oracle(seqalk, oracle, workloads):
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         ok = list(ex.map(check, range(len(ids))))
     assert all(ok), [int(ids[k]) for k, v in enumerate(ok) if not v]
+
+
+def test_job_chunks_and_async_hand_off(seqalk, oracle, workloads):
+    """seqalk_job_set_chunks / run_chunk / start_async + wait_chunk: same results as one run."""
+    import torch
+
+    genes = workloads.mixed(14, seed=3, lo=150, hi=2000)
+    od, op, oh = oracle.all_pairs(genes, 3, 2, want_pair_hashes=True)
+    T = len(op)
+    ends = [10, 10, 37, T]  # includes an empty chunk
+    with seqalk.Job(genes, 3, 2) as job:
+        job.set_chunks(ends)
+        for c in range(len(ends)):
+            job.run_chunk(c)
+        pen, dig = job.fetch()
+        assert np.array_equal(pen, op) and [d.tobytes().hex() for d in dig] == oh
+        pen_t = torch.zeros(T, dtype=torch.int32, device="cuda")
+        dig_t = torch.zeros((T, 64), dtype=torch.uint8, device="cuda")
+        job.start_async(pen_t.data_ptr(), dig_t.data_ptr())
+        lo = 0
+        for c, hi in enumerate(ends):
+            job.wait_chunk(c, torch.cuda.current_stream().cuda_stream)
+            part = pen_t[lo:hi].cpu().numpy()  # ordered after the chunk by the stream wait
+            assert np.array_equal(part, op[lo:hi])
+            lo = hi
+        job.finish_async()
+        assert [bytes(r).hex() for r in dig_t.cpu().numpy()] == oh

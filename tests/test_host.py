@@ -139,3 +139,16 @@ def test_alignment_strings_strip_scan(seqalk):
     x = np.array([0, 95, 95, 65, 95], dtype=np.int32)
     y = np.array([0, 95, 95, 95, 67], dtype=np.int32)
     assert seqalk.alignment_strings(x, y) == (b"A_", b"_C")
+
+
+def test_partition_chunks_matches_per_chunk_partition(seqalk):
+    lens = [100, 2000, 350, 900, 1200, 60, 777, 5000, 41, 3000]
+    T = seqalk.num_tasks(len(lens))
+    for nranks, nchunks in [(1, 1), (3, 4), (8, 2)]:
+        chunks = seqalk.partition_chunks(lens, nranks, nchunks)
+        assert len(chunks) == nchunks and all(len(c) == nranks for c in chunks)
+        seen = np.concatenate([a for c in chunks for a in c])
+        assert np.array_equal(np.sort(seen), np.arange(T))
+        for c in range(nchunks):
+            ref = seqalk.partition_all(lens, nranks, T * c // nchunks, T * (c + 1) // nchunks)
+            assert all(np.array_equal(a, b) for a, b in zip(ref, chunks[c]))
