@@ -23,6 +23,8 @@ void throw_cuda(cudaError_t e, const char *what, const char *file, int line) {
 
 static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr size_t EV = 6;  // timing events per batch
+// bounds the descriptor staging of a batch of very many tiny pairs (56 B + strips per pair)
+constexpr size_t MAX_PAIRS_PER_BATCH = 1u << 18;
 
 void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
   k = k_;
@@ -327,7 +329,8 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
                                : (uint64_t)ns * strip_dir_bytes(n, R);
     // what counts against the budget: directions, or (tile mode) checkpoints + kept rows
     const uint64_t bb = tiles_ ? db + brow_ints * 4 : db;
-    if (cur.count && (cur.budget_bytes + bb > dir_budget_ || (uint64_t)cur.nstrips + ns > 0x7fffffffull)) {
+    if (cur.count && (cur.budget_bytes + bb > dir_budget_ || (uint64_t)cur.nstrips + ns > 0x7fffffffull ||
+                      cur.count >= MAX_PAIRS_PER_BATCH)) {
       batches_.push_back(cur);
       cur = Batch{t, 0, 0, 0, 0, 0, 0};
     }

@@ -402,3 +402,12 @@ def test_job_chunks_and_async_hand_off(seqalk, oracle, workloads):
             lo = hi
         job.finish_async()
         assert [bytes(r).hex() for r in dig_t.cpu().numpy()] == oh
+
+
+def test_many_tiny_sequences(seqalk, oracle):
+    """k = 400 sequences of 1..40 letters: 79 800 pairs, most of them far smaller than one strip."""
+    rnd = random.Random(8)
+    genes = [bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(1, 40))) for _ in range(400)]
+    digest, pen = seqalk.get_minimum_penalties(genes, 3, 2)
+    od, op, _ = oracle.all_pairs(genes, 3, 2)
+    assert digest == od and np.array_equal(pen, op)
