@@ -179,7 +179,8 @@ def main():
     cells = workloads.total_cells(genes)
     T = len(genes) * (len(genes) - 1) // 2
     # chunks of task ids: rank 0 folds the hash chain of chunk c while the GPUs work on chunk c+1
-    nchunks = args.nchunks or (8 if T >= 4096 else 1)
+    # (chunks of >= 32k tasks: smaller ones only add kernel tails)
+    nchunks = args.nchunks or max(1, min(8, T // 32768))
 
     def barrier():
         torch.cuda.synchronize()

@@ -40,7 +40,8 @@ class SeqalkError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # SEQALK_LIB: another build of the same library (A/B measurements of kernel changes)
+    return os.environ.get("SEQALK_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 class _Stats(ctypes.Structure):
