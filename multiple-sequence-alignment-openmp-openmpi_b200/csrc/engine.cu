@@ -573,6 +573,8 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.brow = fa.brow;
     ta.mode = variant_.mode;
     ta.addmode = variant_.addmode;
+    ta.long_pairs = few_pairs_ ? 1 : 0;
+    if (const char *e = std::getenv("SEQALK_TB_LONG")) ta.long_pairs = std::atoi(e) ? 1 : 0;
     SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));
 

@@ -49,6 +49,7 @@ struct TracebackArgs {
   const int32_t *brow;      // tile mode: kept boundary rows (one per 256 DP rows)
   int32_t mode;             // tile mode: MODE_* of the recompute (same arithmetic as the fill)
   int32_t addmode;          // tile mode: 2 = IDP.4A cost lookup in the recompute
+  int32_t long_pairs;       // tile mode: 1 = four warps per pair (walk + look-ahead recompute)
   const PairDesc *pairs;
   uint32_t npairs;
   const uint8_t *dirs;

@@ -46,171 +46,317 @@ struct BackWriter0 {
 
 }  // namespace
 
+// Per-pair constants of the tile traceback.
+struct TileCtx {
+  int m, n, nq;
+  uint64_t bstride, mpad;
+  int A, B;
+  const uint8_t *xs, *ys;      // raw characters (output)
+  const uint8_t *xop;          // row operands: letter codes (MODE_TAB) or raw characters
+  const unsigned *yw32;        // y as 4-byte words (codes or raw)
+  const int32_t *brow, *ck;    // kept rows, column checkpoints
+};
+
+template <int MODE>
+__device__ __forceinline__ TileCtx make_ctx(const TracebackArgs &a, const PairDesc &P) {
+  TileCtx T;
+  T.m = P.m;
+  T.n = P.n;
+  T.nq = (P.n + 3) >> 2;
+  T.bstride = (uint64_t)(4 * T.nq + 4);
+  T.mpad = (uint64_t)P.nstrips * 32 * (uint64_t)a.R;  // rows padded to the fill's strips
+  T.A = -2 * a.pgap;
+  T.B = a.pxy - 2 * a.pgap;
+  T.xs = a.seq + P.x_off;
+  T.ys = a.seq + P.y_off;
+  const uint8_t *opbase = (MODE == MODE_TAB) ? a.codes : a.seq;
+  T.xop = opbase + P.x_off;
+  T.yw32 = reinterpret_cast<const unsigned *>(opbase + P.y_off);
+  T.brow = a.brow + P.brow_off;
+  T.ck = reinterpret_cast<const int32_t *>(a.dirs + P.dir_off);
+  return T;
+}
+
+// Shared-memory image of one tile: direction codes [CKQ][32] + the tile's characters.
+constexpr int TILE_SMEM_BYTES = CKQ * 32 * (int)sizeof(uint2) + 2 * TILE_ROWS;
+
+// Recomputes the directions of tile (hs, cb), macro columns [0, tq) and lanes [0, tmax], into
+// `tile` (one warp).  Same sweep as the fill: lane t owns 8 rows, trails lane t-1 by one macro
+// column; left edge = column checkpoint cb-1, top edge = kept row hs-1.
 template <int MODE, int ADDMODE>
-__global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs a) {
-  extern __shared__ uint2 sdirs[];  // [CKQ][32]: codes of the tile's macro column qc, lane t
-  // the tile's characters, staged once per tile for the walk: x rows, then y columns
-  uint64_t *schars = reinterpret_cast<uint64_t *>(sdirs + CKQ * 32);
-  const uint8_t *sxb = reinterpret_cast<const uint8_t *>(schars);
-  const uint8_t *syb = sxb + TILE_ROWS;
-  const uint32_t *sdirs32 = reinterpret_cast<const uint32_t *>(sdirs);
+__device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb, int tq, int tmax, uint8_t *tile,
+                                               int lane) {
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x;
-  const uint32_t p = blockIdx.x;
-  const PairDesc P = a.pairs[p];
-  const int m = P.m, n = P.n;
-  const int nq = (n + 3) >> 2;
-  const uint64_t bstride = (uint64_t)(4 * nq + 4);
-  const uint64_t mpad = (uint64_t)P.nstrips * 32 * (uint64_t)a.R;  // rows padded to the fill's strips
-  const int A = -2 * a.pgap, B = a.pxy - 2 * a.pgap;
-
-  const uint8_t *__restrict__ xs = a.seq + P.x_off;  // raw characters for the output
-  const uint8_t *__restrict__ ys = a.seq + P.y_off;
-  const uint8_t *__restrict__ opbase = (MODE == MODE_TAB) ? a.codes : a.seq;
-  const uint8_t *__restrict__ xop = opbase + P.x_off;
-  const unsigned *__restrict__ yw32 = reinterpret_cast<const unsigned *>(opbase + P.y_off);
-  const int32_t *__restrict__ brow = a.brow + P.brow_off;
-  const int32_t *__restrict__ ck = reinterpret_cast<const int32_t *>(a.dirs + P.dir_off);
-
-  BackWriter0 w1, w2;
-  w1.init(a.out + P.out_off, (uint32_t)(m + n), lane == 0);
-  w2.init(a.out + P.out_off + P.cap, (uint32_t)(m + n), lane == 0);
-
-  int i = m, j = n;
-  int cost = 0;
-  while (i > 0 && j > 0) {
-    // ---- the tile containing (i, j), cut to the rows <= i and columns <= j
-    const int hs = (i - 1) / TILE_ROWS, cb = (j - 1) / (4 * CKQ);
-    const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ, q0 = cb * CKQ;
-    const int tq = ((j - 1 - col0) >> 2) + 1;  // macro columns needed
-    const int tmax = (i - 1 - row0) / RT;      // last lane needed
-    int xc[RT], h[RT];
-    {
-      const int r0 = row0 + lane * RT;
+  uint2 *sdirs = reinterpret_cast<uint2 *>(tile);
+  uint64_t *schars = reinterpret_cast<uint64_t *>(sdirs + CKQ * 32);
+  const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ, q0 = cb * CKQ;
+  int xc[RT], h[RT];
+  {
+    const int r0 = row0 + lane * RT;
 #pragma unroll
-      for (int r = 0; r < RT; ++r) {
-        const bool inside = r0 + r < m;
-        const int ch = inside ? (int)xop[r0 + r] : 0;
-        xc[r] = row_operand<MODE>(inside, ch, r, A, B);
-      }
-      if (cb > 0) {  // left edge = column checkpoint cb-1
-        const int4 *src = reinterpret_cast<const int4 *>(ck + (uint64_t)(cb - 1) * mpad + (uint64_t)r0);
-        const int4 v0 = __ldcg(src), v1 = __ldcg(src + 1);
-        h[0] = v0.x; h[1] = v0.y; h[2] = v0.z; h[3] = v0.w;
-        h[4] = v1.x; h[5] = v1.y; h[6] = v1.z; h[7] = v1.w;
-      } else {
+    for (int r = 0; r < RT; ++r) {
+      const bool inside = r0 + r < T.m;
+      const int ch = inside ? (int)T.xop[r0 + r] : 0;
+      xc[r] = row_operand<MODE>(inside, ch, r, T.A, T.B);
+    }
+    if (cb > 0) {  // left edge = column checkpoint cb-1
+      const int4 *src = reinterpret_cast<const int4 *>(T.ck + (uint64_t)(cb - 1) * T.mpad + (uint64_t)r0);
+      const int4 v0 = __ldcg(src), v1 = __ldcg(src + 1);
+      h[0] = v0.x; h[1] = v0.y; h[2] = v0.z; h[3] = v0.w;
+      h[4] = v1.x; h[5] = v1.y; h[6] = v1.z; h[7] = v1.w;
+    } else {
 #pragma unroll
-        for (int r = 0; r < RT; ++r) h[r] = 0;
-      }
+      for (int r = 0; r < RT; ++r) h[r] = 0;
     }
-    {  // stage the tile's characters (8 per lane; rows / columns past the ends are never walked)
-      const int r0 = row0 + lane * 8, c0 = col0 + lane * 8;
-      schars[lane] = r0 < m ? *reinterpret_cast<const uint64_t *>(xs + r0) : 0ull;
-      schars[32 + lane] = c0 < n ? *reinterpret_cast<const uint64_t *>(ys + c0) : 0ull;
-    }
-    const int32_t *toprow = hs > 0 ? brow + (uint64_t)(hs - 1) * bstride : nullptr;
-    int dg = __shfl_up_sync(FULL, h[RT - 1], 1);
-    if (lane == 0) dg = (toprow && cb > 0) ? __ldcg(toprow + col0 - 1) : 0;
-    int outv[4] = {0, 0, 0, 0};
-    unsigned yw = 0;
-    int4 top = make_int4(0, 0, 0, 0);
-    unsigned ynext = 0;
-    const int4 *top4 = toprow ? reinterpret_cast<const int4 *>(toprow) + q0 : nullptr;
-    if (lane == 0) {
-      ynext = __ldg(yw32 + q0);
-      if (top4) top = __ldcg(top4);
-    }
-    const int nsteps = tq + tmax;
-    for (int q = 0; q < nsteps; ++q) {
-      int up_in[4];
-      up_in[0] = __shfl_up_sync(FULL, outv[0], 1);
-      up_in[1] = __shfl_up_sync(FULL, outv[1], 1);
-      up_in[2] = __shfl_up_sync(FULL, outv[2], 1);
-      up_in[3] = __shfl_up_sync(FULL, outv[3], 1);
-      unsigned ny = __shfl_up_sync(FULL, yw, 1);
-      if (lane == 0) {
-        up_in[0] = top.x; up_in[1] = top.y; up_in[2] = top.z; up_in[3] = top.w;
-        ny = ynext;
-        if (q + 1 < tq) {  // look-ahead for the next macro column
-          ynext = __ldg(yw32 + q0 + q + 1);
-          if (top4) top = __ldcg(top4 + q + 1);
-        }
-      }
-      const int qc = q - lane;
-      if (qc >= 0 && qc < tq && lane <= tmax) {
-        yw = ny;
-        unsigned bits[RT / 4];
-        macro_step<RT, MODE, ADDMODE, true>(h, dg, xc, up_in, yw, A, B, 1, -1, outv, bits);
-        sdirs[qc * 32 + lane] = make_uint2(bits[0], bits[1]);
-      }
-    }
-    __syncwarp();
-    // ---- walk inside the tile (every lane walks; lane 0 writes)
-    int li = i - 1 - row0, lj = j - 1 - col0;
-    while (li >= 0 && lj >= 0) {
-      const unsigned t = (unsigned)li >> 3, r = (unsigned)li & 7u, qc = (unsigned)lj >> 2, c = (unsigned)lj & 3u;
-      const unsigned idx = c * RT + r;
-      const uint32_t word = sdirs32[(qc * 32 + t) * 2 + (idx >> 4)];
-      const uint32_t code = (word >> (30 - 2 * (idx & 15u))) & 3u;
-      const uint32_t xch = sxb[li], ych = syb[lj];
-      if (!(code & DIR_NOT_DIAG)) {
-        w1.put(xch);
-        w2.put(ych);
-        cost += (xch == ych) ? 0 : a.pxy;
-        --li;
-        --lj;
-      } else if (!(code & DIR_LEFT_BETTER)) {
-        w1.put(xch);
-        w2.put('_');
-        cost += a.pgap;
-        --li;
-      } else {
-        w1.put('_');
-        w2.put(ych);
-        cost += a.pgap;
-        --lj;
-      }
-    }
-    i = row0 + li + 1;
-    j = col0 + lj + 1;
-    __syncwarp();
   }
+  {  // stage the tile's characters (8 per lane; rows / columns past the ends are never walked)
+    const int r0 = row0 + lane * 8, c0 = col0 + lane * 8;
+    schars[lane] = r0 < T.m ? *reinterpret_cast<const uint64_t *>(T.xs + r0) : 0ull;
+    schars[32 + lane] = c0 < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + c0) : 0ull;
+  }
+  const int32_t *toprow = hs > 0 ? T.brow + (uint64_t)(hs - 1) * T.bstride : nullptr;
+  int dg = __shfl_up_sync(FULL, h[RT - 1], 1);
+  if (lane == 0) dg = (toprow && cb > 0) ? __ldcg(toprow + col0 - 1) : 0;
+  int outv[4] = {0, 0, 0, 0};
+  unsigned yw = 0;
+  int4 top = make_int4(0, 0, 0, 0);
+  unsigned ynext = 0;
+  const int4 *top4 = toprow ? reinterpret_cast<const int4 *>(toprow) + q0 : nullptr;
+  if (lane == 0) {
+    ynext = __ldg(T.yw32 + q0);
+    if (top4) top = __ldcg(top4);
+  }
+  const int nsteps = tq + tmax;
+  for (int q = 0; q < nsteps; ++q) {
+    int up_in[4];
+    up_in[0] = __shfl_up_sync(FULL, outv[0], 1);
+    up_in[1] = __shfl_up_sync(FULL, outv[1], 1);
+    up_in[2] = __shfl_up_sync(FULL, outv[2], 1);
+    up_in[3] = __shfl_up_sync(FULL, outv[3], 1);
+    unsigned ny = __shfl_up_sync(FULL, yw, 1);
+    if (lane == 0) {
+      up_in[0] = top.x; up_in[1] = top.y; up_in[2] = top.z; up_in[3] = top.w;
+      ny = ynext;
+      if (q + 1 < tq) {  // look-ahead for the next macro column
+        ynext = __ldg(T.yw32 + q0 + q + 1);
+        if (top4) top = __ldcg(top4 + q + 1);
+      }
+    }
+    const int qc = q - lane;
+    if (qc >= 0 && qc < tq && lane <= tmax) {
+      yw = ny;
+      unsigned bits[RT / 4];
+      macro_step<RT, MODE, ADDMODE, true>(h, dg, xc, up_in, yw, T.A, T.B, 1, -1, outv, bits);
+      sdirs[qc * 32 + lane] = make_uint2(bits[0], bits[1]);
+    }
+  }
+}
+
+// Walks the path inside a recomputed tile from (i, j) until it leaves through the top or the
+// left edge (every lane walks; the writers store from lane 0 only).
+__device__ __forceinline__ void walk_tile(const uint8_t *tile, int row0, int col0, int &i, int &j, int &cost,
+                                          BackWriter0 &w1, BackWriter0 &w2, int pxy, int pgap) {
+  const uint32_t *sdirs32 = reinterpret_cast<const uint32_t *>(tile);
+  const uint8_t *sxb = tile + CKQ * 32 * sizeof(uint2);
+  const uint8_t *syb = sxb + TILE_ROWS;
+  int li = i - 1 - row0, lj = j - 1 - col0;
+  while (li >= 0 && lj >= 0) {
+    const unsigned t = (unsigned)li >> 3, r = (unsigned)li & 7u, qc = (unsigned)lj >> 2, c = (unsigned)lj & 3u;
+    const unsigned idx = c * RT + r;
+    const uint32_t word = sdirs32[(qc * 32 + t) * 2 + (idx >> 4)];
+    const uint32_t code = (word >> (30 - 2 * (idx & 15u))) & 3u;
+    const uint32_t xch = sxb[li], ych = syb[lj];
+    if (!(code & DIR_NOT_DIAG)) {
+      w1.put(xch);
+      w2.put(ych);
+      cost += (xch == ych) ? 0 : pxy;
+      --li;
+      --lj;
+    } else if (!(code & DIR_LEFT_BETTER)) {
+      w1.put(xch);
+      w2.put('_');
+      cost += pgap;
+      --li;
+    } else {
+      w1.put('_');
+      w2.put(ych);
+      cost += pgap;
+      --lj;
+    }
+  }
+  i = row0 + li + 1;
+  j = col0 + lj + 1;
+}
+
+// Tails (only one of i, j is non-zero) and the per-pair result record.
+__device__ __forceinline__ void finish_pair(const TracebackArgs &a, const TileCtx &T, uint32_t p, int i, int j,
+                                            int cost, BackWriter0 &w1, BackWriter0 &w2, bool writer) {
   cost += (i + j) * a.pgap;
   for (; i > 0; --i) {
-    w1.put(xs[i - 1]);
+    w1.put(T.xs[i - 1]);
     w2.put('_');
   }
   for (; j > 0; --j) {
     w1.put('_');
-    w2.put(ys[j - 1]);
+    w2.put(T.ys[j - 1]);
   }
   const uint32_t start = w1.pos;
   w1.finish();
   w2.finish();
-  if (lane == 0) {
+  if (writer) {
     PairAlign res;
     res.start = start;
-    res.len = (uint32_t)(m + n) - start;
+    res.len = (uint32_t)(T.m + T.n) - start;
     a.align[p] = res;
     a.path_cost[p] = cost;
   }
 }
 
-cudaError_t launch_traceback_tiles(const TracebackArgs &args, cudaStream_t stream) {
-  if (args.npairs == 0) return cudaSuccess;
-  const size_t smem = (size_t)CKQ * 32 * sizeof(uint2) + 2 * TILE_ROWS;
-  switch (args.mode) {
-    case MODE_GENERAL: traceback_tiles_kernel<MODE_GENERAL, 0><<<args.npairs, 32, smem, stream>>>(args); break;
-    case MODE_CMP: traceback_tiles_kernel<MODE_CMP, 0><<<args.npairs, 32, smem, stream>>>(args); break;
-    case MODE_TAB:
-      if (args.addmode == 2)
-        traceback_tiles_kernel<MODE_TAB, 2><<<args.npairs, 32, smem, stream>>>(args);
-      else
-        traceback_tiles_kernel<MODE_TAB, 0><<<args.npairs, 32, smem, stream>>>(args);
-      break;
-    default: return cudaErrorInvalidValue;
+// One warp per pair (jobs with many pairs): recompute the part of the tile up-left of the entry
+// cell, walk it, repeat.
+template <int MODE, int ADDMODE>
+__global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x;
+  const uint32_t p = blockIdx.x;
+  const PairDesc P = a.pairs[p];
+  const TileCtx T = make_ctx<MODE>(a, P);
+  BackWriter0 w1, w2;
+  w1.init(a.out + P.out_off, (uint32_t)(T.m + T.n), lane == 0);
+  w2.init(a.out + P.out_off + P.cap, (uint32_t)(T.m + T.n), lane == 0);
+  int i = T.m, j = T.n, cost = 0;
+  while (i > 0 && j > 0) {
+    const int hs = (i - 1) / TILE_ROWS, cb = (j - 1) / (4 * CKQ);
+    const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ;
+    const int tq = ((j - 1 - col0) >> 2) + 1;  // macro columns needed
+    const int tmax = (i - 1 - row0) / RT;      // last lane needed
+    recompute_tile<MODE, ADDMODE>(T, hs, cb, tq, tmax, smem, lane);
+    __syncwarp();
+    walk_tile(smem, row0, col0, i, j, cost, w1, w2, a.pxy, a.pgap);
+    __syncwarp();
+  }
+  finish_pair(a, T, p, i, j, cost, w1, w2, lane == 0);
+}
+
+// Four warps per pair (jobs of a few long pairs, where one warp per pair leaves the GPU idle and
+// the tile chain is pure latency): while warp 0 walks the current tile, warps 1..3 recompute —
+// in full — the up to three tiles the path can enter next (above, left, above-left), so the next
+// tile is already in shared memory when the walk leaves the current one.
+constexpr int LONG_SLOTS = 4;
+template <int MODE, int ADDMODE>
+__global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const TracebackArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_i, s_j;
+  __shared__ int s_tag[LONG_SLOTS][2];  // (hs, cb) held by each slot, hs = -1: empty
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t p = blockIdx.x;
+  const PairDesc P = a.pairs[p];
+  const TileCtx T = make_ctx<MODE>(a, P);
+  BackWriter0 w1, w2;
+  w1.init(a.out + P.out_off, (uint32_t)(T.m + T.n), threadIdx.x == 0);
+  w2.init(a.out + P.out_off + P.cap, (uint32_t)(T.m + T.n), threadIdx.x == 0);
+  int cost = 0;
+  if (threadIdx.x == 0) {
+    s_i = T.m;
+    s_j = T.n;
+    for (int s = 0; s < LONG_SLOTS; ++s) s_tag[s][0] = -1;
+  }
+  __syncthreads();
+  auto full_tq = [&](int cb) { return min(CKQ, T.nq - cb * CKQ); };
+  auto full_tmax = [&](int hs) { return min(31, (T.m - 1 - hs * TILE_ROWS) / RT); };
+  // first tile: warp 1 computes it in full
+  {
+    const int hs = (T.m - 1) / TILE_ROWS, cb = (T.n - 1) / (4 * CKQ);
+    if (warp == 1) {
+      recompute_tile<MODE, ADDMODE>(T, hs, cb, full_tq(cb), full_tmax(hs), smem, lane);
+      if (lane == 0) {
+        s_tag[0][0] = hs;
+        s_tag[0][1] = cb;
+      }
+    }
+  }
+  __syncthreads();
+  for (;;) {
+    const int i = s_i, j = s_j;
+    if (i <= 0 || j <= 0) break;
+    const int hs = (i - 1) / TILE_ROWS, cb = (j - 1) / (4 * CKQ);
+    // slot of the current tile (always present: it was a neighbour of the previous one)
+    int cur = 0;
+    for (int s = 0; s < LONG_SLOTS; ++s)
+      if (s_tag[s][0] == hs && s_tag[s][1] == cb) cur = s;
+    // the three tiles the path can enter next; producer warp w handles candidate w-1
+    const int cand_hs[3] = {hs - 1, hs, hs - 1}, cand_cb[3] = {cb, cb - 1, cb - 1};
+    // slots free for new tiles = those holding neither the current tile nor a candidate
+    int target[3] = {-1, -1, -1};
+    {
+      bool used[LONG_SLOTS];
+      for (int s = 0; s < LONG_SLOTS; ++s) {
+        used[s] = (s == cur);
+        for (int c = 0; c < 3; ++c)
+          if (cand_hs[c] >= 0 && cand_cb[c] >= 0 && s_tag[s][0] == cand_hs[c] && s_tag[s][1] == cand_cb[c])
+            used[s] = true;
+      }
+      for (int c = 0; c < 3; ++c) {
+        if (cand_hs[c] < 0 || cand_cb[c] < 0) continue;
+        bool have = false;
+        for (int s = 0; s < LONG_SLOTS; ++s)
+          if (s_tag[s][0] == cand_hs[c] && s_tag[s][1] == cand_cb[c]) have = true;
+        if (have) continue;
+        for (int s = 0; s < LONG_SLOTS; ++s)
+          if (!used[s]) {
+            used[s] = true;
+            target[c] = s;
+            break;
+          }
+      }
+    }
+    __syncthreads();  // everybody has read the tags before they change
+    if (warp == 0) {
+      int wi = i, wj = j;
+      walk_tile(smem + (size_t)cur * TILE_SMEM_BYTES, hs * TILE_ROWS, cb * 4 * CKQ, wi, wj, cost, w1, w2, a.pxy,
+                a.pgap);
+      if (lane == 0) {
+        s_i = wi;
+        s_j = wj;
+      }
+    } else {
+      const int c = warp - 1;
+      if (target[c] >= 0) {
+        recompute_tile<MODE, ADDMODE>(T, cand_hs[c], cand_cb[c], full_tq(cand_cb[c]), full_tmax(cand_hs[c]),
+                                      smem + (size_t)target[c] * TILE_SMEM_BYTES, lane);
+        if (lane == 0) {
+          s_tag[target[c]][0] = cand_hs[c];
+          s_tag[target[c]][1] = cand_cb[c];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) finish_pair(a, T, p, s_i, s_j, cost, w1, w2, lane == 0);
+}
+
+template <int MODE, int ADDMODE>
+static cudaError_t launch_tiles(const TracebackArgs &args, cudaStream_t stream) {
+  if (args.long_pairs) {
+    const size_t smem = (size_t)LONG_SLOTS * TILE_SMEM_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(traceback_tiles_long_kernel<MODE, ADDMODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    traceback_tiles_long_kernel<MODE, ADDMODE><<<args.npairs, 128, smem, stream>>>(args);
+  } else {
+    traceback_tiles_kernel<MODE, ADDMODE><<<args.npairs, 32, TILE_SMEM_BYTES, stream>>>(args);
   }
   return cudaGetLastError();
+}
+
+cudaError_t launch_traceback_tiles(const TracebackArgs &args, cudaStream_t stream) {
+  if (args.npairs == 0) return cudaSuccess;
+  switch (args.mode) {
+    case MODE_GENERAL: return launch_tiles<MODE_GENERAL, 0>(args, stream);
+    case MODE_CMP: return launch_tiles<MODE_CMP, 0>(args, stream);
+    case MODE_TAB: return args.addmode == 2 ? launch_tiles<MODE_TAB, 2>(args, stream) : launch_tiles<MODE_TAB, 0>(args, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace seqalk
