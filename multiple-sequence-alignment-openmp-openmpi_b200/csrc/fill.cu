@@ -23,11 +23,15 @@
 //         H'[i][j] = match ? H'[i-1][j-1] - 2*pgap
 //                          : min(H'[i-1][j-1] + pxy - 2*pgap, H'[i-1][j], H'[i][j-1])
 //     (comparisons are shift-invariant, so ties break exactly as in the reference);
-//   * per cell a 2-bit code is emitted: bit1 = "not diagonal", bit0 = "left strictly
-//     better than up".  The traceback reads DIAG if !bit1, else LEFT if bit0, else UP —
-//     the reference's priority order (match, mismatch-diag, up, left; :502-531).
-//     128 bits per lane are accumulated in registers and written with one 16 B store;
-//     a warp's store is one contiguous 512 B segment (strip-major, step-skewed layout).
+//   * tile mode (default, EMIT = false): scores only — per cell one IDP.4A (cost-table lookup
+//     + add, FMA pipe) and one VIMNMX3 (ALU pipe); the row of H' is kept every 256 DP rows and
+//     each lane checkpoints its rows every 256 DP columns, from which traceback_tiles.cu
+//     recomputes directions for the tiles on the optimal path only;
+//   * directions mode (EMIT = true): per cell a 2-bit code is emitted: bit1 = "not diagonal",
+//     bit0 = "left strictly better than up".  The traceback reads DIAG if !bit1, else LEFT if
+//     bit0, else UP — the reference's priority order (match, mismatch-diag, up, left;
+//     :502-531).  128 bits per lane are accumulated in registers and written with one 16 B
+//     store; a warp's store is one contiguous 512 B segment (strip-major, step-skewed layout).
 #include <cstdlib>
 
 #include "fill_core.cuh"
@@ -52,8 +56,8 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 
 // EMIT = true : directions mode.  2-bit codes for every cell go to HBM (P.dir_off); the boundary
 //               row buffer holds one row per pair, rewritten in place strip after strip.
-// EMIT = false: tile mode.  Scores only; every 256 DP rows (lanes 15 and 31 for R = 16) the row
-//               of H' is kept (P.brow_off: 2 rows per strip), and every CKQ macro columns each
+// EMIT = false: tile mode.  Scores only; every 256 DP rows (lanes 7, 15, 23, 31 for R = 32) the
+//               row of H' is kept (P.brow_off: R/8 rows per strip), and every CKQ macro columns each
 //               lane stores its R row values (P.dir_off reused as the checkpoint region:
 //               [checkpoint][padded row] int32).  The traceback recomputes directions only for
 //               the 256 x 4*CKQ tiles its path visits (traceback_tiles.cu).
