@@ -76,8 +76,13 @@ int seqalk_partition(const int32_t *lens, int32_t k, int64_t id_begin, int64_t i
 int seqalk_partition_all(const int32_t *lens, int32_t k, int64_t id_begin, int64_t id_end, int32_t nranks,
                          int64_t *ids_out, int64_t *counts_out);
 
-/* The shards of `nchunks` consecutive id ranges (chunk c = ids [T*c/nchunks, T*(c+1)/nchunks))
- * for every rank, computed in parallel: ids_out (capacity T) = chunk 0 rank 0, chunk 0 rank 1,
+/* Chunk boundaries for `ntasks` tasks: bounds_out[nchunks+1], chunk c = ids
+ * [bounds[c], bounds[c+1]).  Equal chunks, except that with >= 4 chunks (and >= 4096 tasks) the last three taper
+ * (6 %, 3 %, 1 %) so that the fold of the final chunk — the only part of the hash chain that
+ * cannot overlap GPU work — stays short. */
+int seqalk_chunk_bounds(int64_t ntasks, int32_t nchunks, int64_t *bounds_out);
+/* The shards of the `nchunks` id ranges of seqalk_chunk_bounds for every rank, computed in
+ * parallel: ids_out (capacity T) = chunk 0 rank 0, chunk 0 rank 1,
  * ..., chunk 1 rank 0, ...; counts_out[nchunks*nranks] in the same order. */
 int seqalk_partition_chunks(const int32_t *lens, int32_t k, int32_t nranks, int32_t nchunks, int64_t *ids_out,
                             int64_t *counts_out);

@@ -27,7 +27,7 @@ import numpy as np
 
 __all__ = [
     "SeqalkError", "lib", "library_path", "getMinimumPenalties", "getMinimumPenalty", "do_MPI_task",
-    "get_minimum_penalties", "get_minimum_penalty", "Job", "JobStats", "partition", "partition_all", "partition_chunks", "task_ij",
+    "get_minimum_penalties", "get_minimum_penalty", "Job", "JobStats", "partition", "partition_all", "partition_chunks", "chunk_bounds", "task_ij",
     "num_tasks", "fold_chain", "sha512_hex", "init", "shutdown", "device_count", "version",
 ]
 
@@ -72,6 +72,7 @@ C_ABI = [
     ("seqalk_task_ij", _c.c_int, [_c.c_int64, _I32P, _I32P]),
     ("seqalk_partition", _c.c_int, [_I32P, _c.c_int32, _c.c_int64, _c.c_int64, _c.c_int32, _c.c_int32, _I64P, _I64P]),
     ("seqalk_partition_all", _c.c_int, [_I32P, _c.c_int32, _c.c_int64, _c.c_int64, _c.c_int32, _I64P, _I64P]),
+    ("seqalk_chunk_bounds", _c.c_int, [_c.c_int64, _c.c_int32, _I64P]),
     ("seqalk_partition_chunks", _c.c_int, [_I32P, _c.c_int32, _c.c_int32, _c.c_int32, _I64P, _I64P]),
     ("seqalk_job_create", _c.c_int, [_c.c_int32, _c.POINTER(_c.c_void_p), _I32P, _c.c_int32, _c.c_int32, _c.c_int32, _I64P, _c.c_int64, _c.POINTER(_c.c_void_p)]),
     ("seqalk_job_run", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
@@ -274,6 +275,13 @@ def partition_all(lens: Iterable[int], nranks: int, id_begin: int = 0,
                                       out.ctypes.data_as(_I64P), counts.ctypes.data_as(_I64P)))
     ends = np.cumsum(counts)
     return [out[e - c:e].copy() for c, e in zip(counts, ends)]
+
+
+def chunk_bounds(ntasks: int, nchunks: int) -> List[int]:
+    """Boundaries of the id chunks (tapered tail, see include/seqalk.h)."""
+    out = np.zeros(nchunks + 1, dtype=np.int64)
+    _check(lib().seqalk_chunk_bounds(int(ntasks), int(nchunks), out.ctypes.data_as(_I64P)))
+    return [int(v) for v in out]
 
 
 def partition_chunks(lens: Iterable[int], nranks: int, nchunks: int) -> List[List[np.ndarray]]:

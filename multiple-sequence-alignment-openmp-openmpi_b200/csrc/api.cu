@@ -373,18 +373,45 @@ int seqalk_partition_all(const int32_t *lens, int32_t k, int64_t id_begin, int64
   }
 }
 
+// Chunk c covers task ids [bounds[c], bounds[c+1]).  With >= 4 chunks the last three taper
+// (6 %, 3 %, 1 % of the tasks): the fold of the final chunk is the only part of the hash chain
+// that cannot hide under GPU work, so it is kept short.
+static void chunk_bounds(int64_t T, int nchunks, std::vector<int64_t> &b) {
+  b.assign((size_t)nchunks + 1, 0);
+  if (nchunks >= 4 && T >= 4096) {
+    const int body = nchunks - 3;
+    const int64_t body_total = T - T * 6 / 100 - T * 3 / 100 - T / 100;
+    for (int c = 0; c <= body; ++c) b[c] = body_total * c / body;
+    b[body + 1] = b[body] + T * 6 / 100;
+    b[body + 2] = b[body + 1] + T * 3 / 100;
+  } else {
+    for (int c = 0; c <= nchunks; ++c) b[c] = T * c / nchunks;
+  }
+  b[nchunks] = T;
+}
+
+int seqalk_chunk_bounds(int64_t ntasks, int32_t nchunks, int64_t *bounds_out) {
+  if (ntasks < 0 || nchunks < 1 || !bounds_out) return fail("bad argument");
+  std::vector<int64_t> b;
+  chunk_bounds(ntasks, nchunks, b);
+  std::copy(b.begin(), b.end(), bounds_out);
+  return 0;
+}
+
 int seqalk_partition_chunks(const int32_t *lens, int32_t k, int32_t nranks, int32_t nchunks, int64_t *ids_out,
                             int64_t *counts_out) {
   try {
     if (!lens || !ids_out || !counts_out || nranks < 1 || nchunks < 1) return fail("bad argument");
     const int64_t T = seqalk_num_tasks(k);
+    std::vector<int64_t> bounds;
+    chunk_bounds(T, nchunks, bounds);
     std::vector<std::vector<std::vector<int64_t>>> per(nchunks);
     std::vector<std::thread> th;
     std::vector<std::string> errs(nchunks);
     for (int c = 0; c < nchunks; ++c)
       th.emplace_back([&, c]() {
         try {
-          partition_lpt(lens, k, T * c / nchunks, T * (c + 1) / nchunks, nranks, per[c]);
+          partition_lpt(lens, k, bounds[c], bounds[c + 1], nranks, per[c]);
         } catch (const std::exception &e) {
           errs[c] = e.what();
         }

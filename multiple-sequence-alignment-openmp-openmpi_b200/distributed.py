@@ -22,7 +22,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import Job, fold_chain, partition_chunks
+from . import Job, chunk_bounds, fold_chain, partition_chunks
 
 ComputeFn = Callable[[Sequence[bytes], int, int, np.ndarray], Tuple[np.ndarray, np.ndarray]]
 
@@ -35,7 +35,7 @@ class ShardPlan:
         T = k * (k - 1) // 2
         nchunks = max(1, min(nchunks, max(T, 1)))
         self.T, self.world = T, world
-        self.bounds = [T * c // nchunks for c in range(nchunks + 1)]
+        self.bounds = chunk_bounds(T, nchunks)  # tapered tail: the last fold is the exposed one
         self.ids: List[List[np.ndarray]] = partition_chunks(lens, world, nchunks)  # one parallel LPT pass
 
     @property

@@ -75,4 +75,6 @@ def test_shard_plan_covers_all_tasks():
     assert np.array_equal(np.sort(seen), np.arange(21))
     for c in range(plan.nchunks):
         ids = np.concatenate(plan.ids[c])
-        assert ids.min() >= plan.bounds[c] and ids.max() < plan.bounds[c + 1]
+        if len(ids):
+            assert ids.min() >= plan.bounds[c] and ids.max() < plan.bounds[c + 1]
+        assert len(ids) == plan.bounds[c + 1] - plan.bounds[c]

@@ -149,6 +149,8 @@ def test_partition_chunks_matches_per_chunk_partition(seqalk):
         assert len(chunks) == nchunks and all(len(c) == nranks for c in chunks)
         seen = np.concatenate([a for c in chunks for a in c])
         assert np.array_equal(np.sort(seen), np.arange(T))
+        b = seqalk.chunk_bounds(T, nchunks)
+        assert b[0] == 0 and b[-1] == T and all(x <= y for x, y in zip(b, b[1:]))
         for c in range(nchunks):
-            ref = seqalk.partition_all(lens, nranks, T * c // nchunks, T * (c + 1) // nchunks)
+            ref = seqalk.partition_all(lens, nranks, b[c], b[c + 1])
             assert all(np.array_equal(a, b) for a, b in zip(ref, chunks[c]))
