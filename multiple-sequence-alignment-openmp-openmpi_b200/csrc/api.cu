@@ -373,17 +373,16 @@ int seqalk_partition_all(const int32_t *lens, int32_t k, int64_t id_begin, int64
   }
 }
 
-// Chunk c covers task ids [bounds[c], bounds[c+1]).  With >= 4 chunks the last three taper
-// (6 %, 3 %, 1 % of the tasks): the fold of the final chunk is the only part of the hash chain
-// that cannot hide under GPU work, so it is kept short.
+// Chunk c covers task ids [bounds[c], bounds[c+1]).  With >= 4 chunks (and a large job) the
+// last chunk holds only 4 % of the tasks: the fold of the final chunk is the only part of the
+// hash chain that cannot hide under GPU work, so it is kept short — but not split further,
+// because very small chunks cost more in kernel tails than their fold saves (measured at 8 GPUs).
 static void chunk_bounds(int64_t T, int nchunks, std::vector<int64_t> &b) {
   b.assign((size_t)nchunks + 1, 0);
   if (nchunks >= 4 && T >= 4096) {
-    const int body = nchunks - 3;
-    const int64_t body_total = T - T * 6 / 100 - T * 3 / 100 - T / 100;
+    const int body = nchunks - 1;
+    const int64_t body_total = T - T * 4 / 100;
     for (int c = 0; c <= body; ++c) b[c] = body_total * c / body;
-    b[body + 1] = b[body] + T * 6 / 100;
-    b[body + 2] = b[body + 1] + T * 3 / 100;
   } else {
     for (int c = 0; c <= nchunks; ++c) b[c] = T * c / nchunks;
   }
