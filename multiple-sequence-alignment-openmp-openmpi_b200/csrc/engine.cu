@@ -290,6 +290,8 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
       if (std::atoi(e) == 16) variant_.R = 16;
   }
   variant_.emit = !tiles_;
+  for (const TaskIJ &tk : tasks_)
+    if (tk.i < 0 || tk.i >= pack_->k || tk.j < 0 || tk.j >= pack_->k) throw std::runtime_error("task index out of range");
   {
     // few long pairs: the GPU is filled by the strips of the same pair running as a wavefront,
     // so use thinner strips (more of them) and publish progress more often
