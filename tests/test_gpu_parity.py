@@ -72,6 +72,12 @@ def test_driver_stdin_stdout_bytes(load_fixture, workloads):
         lines = out.split("\n")
         assert lines[0].startswith("Time: ") and lines[0].endswith(" us")
         assert "\n".join(lines[1:]) == e["digest"] + "\n" + "".join(f"{p} " for p in e["penalties"]) + "\n"
+    # any whitespace separates tokens (operator>> semantics), no trailing newline needed
+    pxy, pgap, genes, e = load_fixture("mseq")
+    doc = b"\t3 \r\n 2\n\n3  " + b" \t ".join(genes)
+    out = subprocess.run([exe], input=doc, stdout=subprocess.PIPE, check=True,
+                         env=dict(os.environ, SEQALK_GPUS="1")).stdout.decode().split("\n")
+    assert out[1] == e["digest"] and out[2] == "5 4 9 "
 
 
 # ---------------------------------------------------------------- oracle parity, seeded
