@@ -290,6 +290,8 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
       if (std::atoi(e) == 16) variant_.R = 16;
   }
   variant_.emit = !tiles_;
+  mixed_ = tiles_;  // 512-row last strips where they halve the row padding
+  if (const char *e = std::getenv("SEQALK_MIXED")) mixed_ = tiles_ && std::atoi(e) != 0;
   for (const TaskIJ &tk : tasks_)
     if (tk.i < 0 || tk.i >= pack_->k || tk.j < 0 || tk.j >= pack_->k) throw std::runtime_error("task index out of range");
   {
@@ -323,11 +325,12 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     if (m < 1 || n < 1)
       throw std::runtime_error("empty sequence: undefined in the reference (ceil(0/0) tile size, submit/xuliny-seqalkway.cpp:457)");
     maxlen = std::max<int64_t>(maxlen, std::max(m, n));
-    const uint32_t ns = (uint32_t)num_strips(m, R);
-    const uint64_t brow_ints = tiles_ ? (uint64_t)(R / 8) * ns * (4ull * (uint64_t)macro_cols(n) + 4)
+    const StripGeom geo = strip_geometry(m, R, mixed_);
+    const uint32_t ns = (uint32_t)geo.nstrips;
+    const uint64_t brow_ints = tiles_ ? (uint64_t)(geo.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(n) + 4)
                                       : 4ull * (uint64_t)macro_cols(n) + 4;
-    // directions, or (tile mode) the column checkpoints [nq / CKQ][rows padded to the strip]
-    const uint64_t db = tiles_ ? (uint64_t)(macro_cols(n) / CKQ) * ns * (32ull * R) * 4 + 16
+    // directions, or (tile mode) the column checkpoints [nq / CKQ][rows padded to the strips]
+    const uint64_t db = tiles_ ? (uint64_t)(macro_cols(n) / CKQ) * geo.mpad * 4 + 16
                                : (uint64_t)ns * strip_dir_bytes(n, R);
     // what counts against the budget: directions, or (tile mode) checkpoints + kept rows
     const uint64_t bb = tiles_ ? db + brow_ints * 4 : db;
@@ -461,7 +464,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ensure(S.out, need_.out_bytes + BUFFER_SLACK);
     ensure(S.align, need_.count * sizeof(PairAlign));
     ensure(S.cost, need_.count * sizeof(int32_t));
-    ensure(S.counter, sizeof(uint32_t));
+    ensure(S.counter, 2 * sizeof(uint32_t));
     // ---- build descriptors in pinned staging
     const size_t pairs_bytes = round_up(need_.count * sizeof(PairDesc), 256);
     const size_t tasks_bytes = round_up((size_t)need_.nstrips * sizeof(StripTask), 256);
@@ -498,14 +501,17 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       d.brow_off = brow_off;
       d.out_off = out_off;
       d.strip0 = strip0;
-      d.nstrips = num_strips(d.m, R);
+      const StripGeom geo = strip_geometry(d.m, R, mixed_);
+      d.nstrips = geo.nstrips;
+      d.mpad = geo.mpad;
+      d.half_last = geo.half_last;
       d.cap = (uint32_t)round_up((size_t)d.m + d.n, 16);
       d.task_id = (int32_t)t_index;
       hp[p] = d;
       hs[p] = result_slots_.empty() ? (uint32_t)t_index : result_slots_[t_index];
       if (tiles_) {
-        dir_off += round_up((uint64_t)(macro_cols(d.n) / CKQ) * d.nstrips * (32ull * R) * 4, 16);
-        brow_off += (uint64_t)(R / 8) * d.nstrips * (4ull * (uint64_t)macro_cols(d.n) + 4);
+        dir_off += round_up((uint64_t)(macro_cols(d.n) / CKQ) * d.mpad * 4, 16);
+        brow_off += (uint64_t)(d.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(d.n) + 4);
       } else {
         dir_off += (uint64_t)d.nstrips * strip_dir_bytes(d.n, R);
         brow_off += 4ull * (uint64_t)macro_cols(d.n) + 4;
@@ -514,12 +520,17 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       strip0 += (uint32_t)d.nstrips;
       max_strips = std::max(max_strips, d.nstrips);
     }
-    // strip queue ordered (strip, pair): a strip's predecessor is always claimed earlier
+    // strip queue ordered (strip, pair): a strip's predecessor is always claimed earlier.
+    // Half-height last strips (tile mode) go to the end: they run in a second launch with the
+    // 16-rows-per-lane kernel, after all their predecessors have finished.
+    size_t n_main = 0, n_half = 0;
     {
-      size_t w = 0;
       for (int s = 0; s < max_strips; ++s)
         for (size_t p = 0; p < B.count; ++p)
-          if (s < hp[p].nstrips) ht[w++] = StripTask{(uint32_t)p, (uint32_t)s};
+          if (s < hp[p].nstrips && !(hp[p].half_last && s == hp[p].nstrips - 1))
+            ht[n_main++] = StripTask{(uint32_t)p, (uint32_t)s};
+      for (size_t p = 0; p < B.count; ++p)
+        if (hp[p].half_last) ht[n_main + n_half++] = StripTask{(uint32_t)p, (uint32_t)(hp[p].nstrips - 1)};
     }
     S.last_pairs.assign(hp, hp + B.count);
     // ---- enqueue: fill stream
@@ -533,7 +544,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     SEQALK_CUDA(cudaMemcpyAsync(S.slots.p, hs, B.count * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SEQALK_CUDA(cudaEventRecord(S.staged, st));
     S.staged_pending = true;
-    SEQALK_CUDA(cudaMemsetAsync(S.counter.p, 0, sizeof(uint32_t), st));
+    SEQALK_CUDA(cudaMemsetAsync(S.counter.p, 0, 2 * sizeof(uint32_t), st));
     SEQALK_CUDA(cudaMemsetAsync(S.progress.p, 0, (size_t)B.nstrips * sizeof(uint32_t), st));
 
     FillArgs fa;
@@ -543,7 +554,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.publish_shift = few_pairs_ ? PUBLISH_SHIFT_FEW : PUBLISH_SHIFT_MANY;
     fa.pairs = static_cast<const PairDesc *>(S.pairs.p);
     fa.tasks = static_cast<const StripTask *>(S.tasks.p);
-    fa.ntasks = B.nstrips;
+    fa.ntasks = (uint32_t)n_main;
     fa.counter = static_cast<uint32_t *>(S.counter.p);
     fa.progress = static_cast<uint32_t *>(S.progress.p);
     fa.brow = static_cast<int32_t *>(S.brow.p);
@@ -552,6 +563,17 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.pgap = pgap_;
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 0], st));
     SEQALK_CUDA(launch_fill(fa, variant_, sm_count_, st));
+    if (n_half) {  // second launch: the 512-row last strips
+      FillArgs fh = fa;
+      fh.tasks = fa.tasks + n_main;
+      fh.ntasks = (uint32_t)n_half;
+      fh.counter = fa.counter + 1;
+      FillVariant vh = variant_;
+      vh.R = 16;
+      vh.minb = 0;
+      SEQALK_CUDA(launch_fill(fh, vh, sm_count_, st));
+      stats_.fill_launches++;
+    }
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 1], st));
     SEQALK_CUDA(cudaEventRecord(S.fill_done, st));
     // ---- enqueue: post stream (high priority; runs under the next batch's fill).  In tile

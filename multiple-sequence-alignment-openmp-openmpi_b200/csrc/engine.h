@@ -135,6 +135,7 @@ class DeviceWorker {
   int pxy_ = 0, pgap_ = 0;
   FillVariant variant_;
   bool few_pairs_ = false;  // fewer strips than ~2x the resident warps: wavefront-bound job
+  bool mixed_ = false;  // tile mode, R = 32: half-height last strips (second fill launch)
   bool tiles_ = false;  // tile mode: score-only fill + checkpoints, directions recomputed per tile
   Batch need_{0, 0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches
   DevBuf res_pen_, res_dig_;

@@ -62,7 +62,8 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 //               [checkpoint][padded row] int32).  The traceback recomputes directions only for
 //               the 256 x 4*CKQ tiles its path visits (traceback_tiles.cu).
 template <int R, int MODE, int ADDMODE, bool EMIT>
-__device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc &P, const int s, const int lane) {
+__device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc &P, const int s, const int row_base,
+                                              const int lane) {
   constexpr int G = EMIT ? 16 / R : 2;  // macro steps per loop iteration (per 16 B direction store)
   const unsigned FULL = 0xffffffffu;
   const int m = P.m, n = P.n;
@@ -79,16 +80,16 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   const uint64_t bstride = EMIT ? 0 : (uint64_t)(4 * nq + 4);
   int32_t *bbase = a.brow + P.brow_off;
   const int4 *__restrict__ brow_rd =
-      reinterpret_cast<const int4 *>(EMIT ? bbase : bbase + (uint64_t)(first ? 0 : s * (R / 8) - 1) * bstride);
+      reinterpret_cast<const int4 *>(EMIT ? bbase : bbase + (uint64_t)(first ? 0 : row_base / TILE_ROWS - 1) * bstride);
   int4 *__restrict__ brow_wr = reinterpret_cast<int4 *>(
-      EMIT ? bbase : bbase + (uint64_t)(s * (R / 8) + (lane * R) / TILE_ROWS) * bstride);  // kept row (DP row / 256) - 1
+      EMIT ? bbase : bbase + (uint64_t)((row_base + lane * R) / TILE_ROWS) * bstride);  // kept row (DP row / 256) - 1
   uint4 *__restrict__ dout =
       reinterpret_cast<uint4 *>(a.dirs + P.dir_off + (uint64_t)s * ((uint64_t)ngroups * 512ull)) + lane;
   const unsigned *prev_progress = a.progress + P.strip0 + (first ? 0 : s - 1);
   unsigned *my_progress = a.progress + P.strip0 + s;
 
   // this lane's rows
-  const int row0 = s * (32 * R) + lane * R;
+  const int row0 = row_base + lane * R;
   int xc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -97,7 +98,7 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
     xc[r] = row_operand<MODE>(inside, ch, r, A, B);
   }
   // tile mode: column checkpoints of this lane's rows, [checkpoint][padded row]
-  const uint64_t mpad = (uint64_t)P.nstrips * (32 * R);
+  const uint64_t mpad = (uint64_t)P.mpad;
   int4 *__restrict__ ck_wr = reinterpret_cast<int4 *>(a.dirs + P.dir_off) + (uint64_t)row0 / 4;
 
   int h[R];
@@ -221,7 +222,11 @@ __global__ void __launch_bounds__(FILL_THREADS, MINB) fill_kernel(const FillArgs
     if (t >= a.ntasks) break;
     const StripTask task = a.tasks[t];
     const PairDesc P = a.pairs[task.pair];
-    process_strip<R, MODE, ADDMODE, EMIT>(a, P, (int)task.strip, lane);
+    const int s = (int)task.strip;
+    // a pair's 512-row last strip (tile mode, see strip_geometry) is run by the R = 16 kernel
+    // in a second, small launch; it starts where the 1024-row strips end
+    const int row_base = (!EMIT && P.half_last && s == P.nstrips - 1) ? (int)P.mpad - 512 : s * (32 * R);
+    process_strip<R, MODE, ADDMODE, EMIT>(a, P, s, row_base, lane);
   }
 }
 

@@ -23,6 +23,8 @@ struct PairDesc {
   int32_t nstrips;     // ceil(m / (32*R))
   uint32_t cap;        // bytes per alignment buffer = round16(m + n)
   int32_t task_id;     // position in the reference's task order (for result placement)
+  uint32_t mpad;       // rows padded to the strips (stride of the tile-mode column checkpoints)
+  uint32_t half_last;  // tile mode, R = 32: the last strip has 512 rows (16 per lane) instead of 1024
 };
 
 struct StripTask {
@@ -51,6 +53,24 @@ __host__ __device__ inline uint64_t strip_dir_bytes(int n, int R) {
   return (uint64_t)strip_groups(n, R) * 512ull;
 }
 __host__ __device__ inline int num_strips(int m, int R) { return (m + strip_rows(R) - 1) / strip_rows(R); }
+
+// Strip geometry of a pair: all strips have 32*R rows, except that with `mixed` (tile mode,
+// R = 32) a last strip covering <= 512 remaining rows is a half strip of 16 rows per lane —
+// halves the average row padding (5.0 % -> 2.5 % of the cells on BASELINE config 4).
+struct StripGeom {
+  int nstrips;
+  uint32_t mpad;
+  uint32_t half_last;
+};
+__host__ __device__ inline StripGeom strip_geometry(int m, int R, bool mixed) {
+  StripGeom g;
+  const int h = strip_rows(R);
+  g.nstrips = (m + h - 1) / h;
+  const int rem = m - (g.nstrips - 1) * h;  // rows of the last strip, 1..h
+  g.half_last = (mixed && R == 32 && rem <= h / 2) ? 1u : 0u;
+  g.mpad = (uint32_t)((g.nstrips - 1) * h + (g.half_last ? h / 2 : h));
+  return g;
+}
 
 // Direction codes.  16 cells per 32-bit word, shifted in MSB-first in the order
 // idx = c*R + r (column-major inside the lane's R x 4 block).

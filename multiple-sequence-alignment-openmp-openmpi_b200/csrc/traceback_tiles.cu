@@ -64,7 +64,7 @@ __device__ __forceinline__ TileCtx make_ctx(const TracebackArgs &a, const PairDe
   T.n = P.n;
   T.nq = (P.n + 3) >> 2;
   T.bstride = (uint64_t)(4 * T.nq + 4);
-  T.mpad = (uint64_t)P.nstrips * 32 * (uint64_t)a.R;  // rows padded to the fill's strips
+  T.mpad = (uint64_t)P.mpad;  // rows padded to the fill's strips
   T.A = -2 * a.pgap;
   T.B = a.pxy - 2 * a.pgap;
   T.xs = a.seq + P.x_off;

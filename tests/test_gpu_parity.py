@@ -282,7 +282,7 @@ def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatc
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     rnd = random.Random(17)
-    lens = [1, 5, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1030, 2049]
+    lens = [1, 5, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1025, 1030, 1536, 1537, 2049, 2560]
     genes = [bytes(rnd.choice(b"ACGT") for _ in range(L)) for L in lens]
     with seqalk.Job(genes, 3, 2) as job:  # a fresh worker picks the env up
         job.run()
