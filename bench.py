@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "multiple-sequence-alignment-openmp-openmpi_b200"
 OPS_PER_CELL = 10  # algorithmic int32 lane-ops per DP cell
+EXECUTED_PER_CELL = 2.67  # lane-instructions the tile-mode fill executes per cell (ncu, profiles/)
 
 
 def parse_args():
@@ -305,6 +306,16 @@ def main():
                 "peak_nominal_at_sm_mhz": 148 * 64 * sm_mhz * 1e6 / 1e9 if sm_mhz else None,
                 "issue_rates_gops": {k: v / 1e9 for k, v in peaks.items()},
                 "fill_gcups_per_gpu": agg_ops_rate / world / OPS_PER_CELL / 1e9,
+                # the same kernel against the machine's real issue ceiling: executed warp
+                # instructions per cell from the committed ncu capture (tile-mode fill: 2.67
+                # lane-instructions per cell incl. loop bookkeeping) vs the measured ALU+FMA
+                # dual-issue rate (LOP3+IMAD microbenchmark)
+                "issue": {"lane_instr_per_cell": EXECUTED_PER_CELL,
+                          "achieved": agg_ops_rate / world / OPS_PER_CELL * EXECUTED_PER_CELL / 1e9,
+                          "peak": peaks["lop3+imad"] / 1e9, "unit": "Ginstr/s",
+                          "frac": (agg_ops_rate / world / OPS_PER_CELL * EXECUTED_PER_CELL) / peaks["lop3+imad"]
+                          if tile_mode else None,
+                          "source": "profiles/r01_fill_tiles_cfg4_ncu_summary.txt"},
                 "fill_ms_per_step_max_rank": fill_ms_max,
                 "hbm": {"bound": "hbm", "achieved": agg_dir_rate / world / 1e9, "unit": "GB/s",
                         "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
