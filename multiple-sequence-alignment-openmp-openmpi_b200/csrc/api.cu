@@ -9,6 +9,8 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 #include <vector>
 
@@ -127,6 +129,125 @@ struct DeviceArray {
     cudaFree(p);
   }
 };
+
+// Chunk c covers task ids [bounds[c], bounds[c+1]).  With >= 4 chunks (and a large job) the
+// last chunk holds only 4 % of the tasks: the fold of the final chunk is the only part of the
+// hash chain that cannot hide under GPU work, so it is kept short — but not split further,
+// because very small chunks cost more in kernel tails than their fold saves (measured at 8 GPUs).
+void chunk_bounds(int64_t T, int nchunks, std::vector<int64_t> &b) {
+  b.assign((size_t)nchunks + 1, 0);
+  if (nchunks >= 4 && T >= 4096) {
+    const int body = nchunks - 1;
+    const int64_t body_total = T - T * 4 / 100;
+    for (int c = 0; c <= body; ++c) b[c] = body_total * c / body;
+  } else {
+    for (int c = 0; c <= nchunks; ++c) b[c] = T * c / nchunks;
+  }
+  b[nchunks] = T;
+}
+
+// Shards of every chunk for every rank, one thread per chunk: per[c][r] = increasing task ids.
+void partition_all_chunks(const int32_t *lens, int k, int nranks, const std::vector<int64_t> &bounds,
+                          std::vector<std::vector<std::vector<int64_t>>> &per) {
+  const int nchunks = (int)bounds.size() - 1;
+  per.assign((size_t)nchunks, {});
+  std::vector<std::thread> th;
+  std::vector<std::string> errs((size_t)nchunks);
+  for (int c = 0; c < nchunks; ++c)
+    th.emplace_back([&, c]() {
+      try {
+        partition_lpt(lens, k, bounds[c], bounds[c + 1], nranks, per[c]);
+      } catch (const std::exception &e) {
+        errs[c] = e.what();
+      }
+    });
+  for (std::thread &t : th) t.join();
+  for (const std::string &e : errs)
+    if (!e.empty()) throw std::runtime_error(e);
+}
+
+// All pairs on N >= 2 GPUs of this process with the fused gather: every GPU runs its
+// cell-balanced share of each chunk of task ids; its digest kernel stores the results straight
+// into GPU 0's task-ordered arrays (peer stores over NVLink); the host folds chunk c while the
+// GPUs work on chunk c+1.
+void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, int32_t *penalties,
+                    char digest_hex[129]) {
+  const int N = (int)r.workers.size();
+  const int64_t T = (int64_t)k * (k - 1) / 2;
+  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(8, T / 32768));
+  // SEQALK_TRACE=1: phase times of this call on stderr
+  const bool trace = std::getenv("SEQALK_TRACE") && std::atoi(std::getenv("SEQALK_TRACE"));
+  const auto t0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char *what, int a = -1) {
+    if (!trace) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (a >= 0)
+      std::fprintf(stderr, "[seqalk] %9.2f ms  %s %d\n", ms, what, a);
+    else
+      std::fprintf(stderr, "[seqalk] %9.2f ms  %s\n", ms, what);
+  };
+  std::vector<int64_t> bounds;
+  chunk_bounds(T, nchunks, bounds);
+  std::vector<std::vector<std::vector<int64_t>>> per;
+  partition_all_chunks(pack.len.data(), k, N, bounds, per);
+  mark("partitioned");
+  DeviceArray pen0(0, (size_t)T * sizeof(int32_t)), dig0(0, (size_t)T * 64);
+  for (int d = 0; d < N; ++d) {
+    std::vector<TaskIJ> tasks;
+    std::vector<uint32_t> slots;
+    std::vector<size_t> ends;
+    for (int c = 0; c < nchunks; ++c) {
+      for (int64_t id : per[c][d]) {
+        TaskIJ t;
+        task_from_id(id, &t.i, &t.j);
+        tasks.push_back(t);
+        slots.push_back((uint32_t)id);
+      }
+      ends.push_back(tasks.size());
+    }
+    DeviceWorker &w = *r.workers[d];
+    w.load(pack);
+    mark("loaded on GPU", d);
+    w.plan(tasks, pxy, pgap, &slots, &ends);
+    mark("planned on GPU", d);
+    w.start_async(static_cast<int32_t *>(pen0.p), static_cast<uint8_t *>(dig0.p));
+  }
+  std::vector<uint8_t> digests((size_t)T * 64);
+  size_t hl = 0;
+  digest_hex[0] = 0;
+  std::thread folder;
+  std::string error;
+  try {
+    for (int c = 0; c < nchunks; ++c) {
+      for (int d = 0; d < N; ++d) {
+        r.workers[d]->wait_chunk((size_t)c, nullptr);
+        mark("chunk done on GPU", d);
+      }
+      const size_t lo = (size_t)bounds[c], n = (size_t)(bounds[c + 1] - bounds[c]);
+      if (!n) continue;
+      SEQALK_CUDA(cudaSetDevice(0));
+      SEQALK_CUDA(cudaMemcpy(penalties + lo, static_cast<int32_t *>(pen0.p) + lo, n * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost));
+      SEQALK_CUDA(cudaMemcpy(digests.data() + 64 * lo, static_cast<uint8_t *>(dig0.p) + 64 * lo, n * 64,
+                             cudaMemcpyDeviceToHost));
+      if (folder.joinable()) folder.join();
+      mark("folding chunk", c);
+      folder = std::thread([&, lo, n]() { fold_chain(digests.data() + 64 * lo, n, digest_hex, &hl); });
+    }
+  } catch (const std::exception &e) {
+    error = e.what();
+  }
+  if (folder.joinable()) folder.join();
+  mark("folded");
+  for (int d = 0; d < N; ++d) {
+    try {
+      r.workers[d]->finish_async();
+    } catch (const std::exception &e) {
+      if (error.empty()) error = "GPU " + std::to_string(d) + ": " + e.what();
+    }
+  }
+  if (!error.empty()) throw std::runtime_error(error);
+}
 
 // all tasks of `tasks` on the runtime's GPUs; results in task order on the host
 void run_tasks(Runtime &r, const SeqPack &pack, const std::vector<TaskIJ> &tasks, int pxy, int pgap,
@@ -285,6 +406,10 @@ int seqalk_all_pairs(const char *const *seqs, const int32_t *lens, int32_t k, in
       w.run_and_fold(penalties_out, digest_hex_out);
       return 0;
     }
+    if (r.peer_ok) {
+      all_pairs_peer(r, pack, k, pxy, pgap, penalties_out, digest_hex_out);
+      return 0;
+    }
     std::vector<uint8_t> digests(tasks.size() * 64);
     run_tasks(r, pack, tasks, pxy, pgap, penalties_out, digests.data());
     size_t hl = 0;
@@ -373,22 +498,6 @@ int seqalk_partition_all(const int32_t *lens, int32_t k, int64_t id_begin, int64
   }
 }
 
-// Chunk c covers task ids [bounds[c], bounds[c+1]).  With >= 4 chunks (and a large job) the
-// last chunk holds only 4 % of the tasks: the fold of the final chunk is the only part of the
-// hash chain that cannot hide under GPU work, so it is kept short — but not split further,
-// because very small chunks cost more in kernel tails than their fold saves (measured at 8 GPUs).
-static void chunk_bounds(int64_t T, int nchunks, std::vector<int64_t> &b) {
-  b.assign((size_t)nchunks + 1, 0);
-  if (nchunks >= 4 && T >= 4096) {
-    const int body = nchunks - 1;
-    const int64_t body_total = T - T * 4 / 100;
-    for (int c = 0; c <= body; ++c) b[c] = body_total * c / body;
-  } else {
-    for (int c = 0; c <= nchunks; ++c) b[c] = T * c / nchunks;
-  }
-  b[nchunks] = T;
-}
-
 int seqalk_chunk_bounds(int64_t ntasks, int32_t nchunks, int64_t *bounds_out) {
   if (ntasks < 0 || nchunks < 1 || !bounds_out) return fail("bad argument");
   std::vector<int64_t> b;
@@ -404,20 +513,8 @@ int seqalk_partition_chunks(const int32_t *lens, int32_t k, int32_t nranks, int3
     const int64_t T = seqalk_num_tasks(k);
     std::vector<int64_t> bounds;
     chunk_bounds(T, nchunks, bounds);
-    std::vector<std::vector<std::vector<int64_t>>> per(nchunks);
-    std::vector<std::thread> th;
-    std::vector<std::string> errs(nchunks);
-    for (int c = 0; c < nchunks; ++c)
-      th.emplace_back([&, c]() {
-        try {
-          partition_lpt(lens, k, bounds[c], bounds[c + 1], nranks, per[c]);
-        } catch (const std::exception &e) {
-          errs[c] = e.what();
-        }
-      });
-    for (std::thread &t : th) t.join();
-    for (const std::string &e : errs)
-      if (!e.empty()) return fail(e.c_str());
+    std::vector<std::vector<std::vector<int64_t>>> per;
+    partition_all_chunks(lens, k, nranks, bounds, per);
     int64_t *w = ids_out;
     for (int c = 0; c < nchunks; ++c)
       for (int r = 0; r < nranks; ++r) {
