@@ -256,20 +256,6 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   pgap_ = pgap;
   batches_.clear();
   stats_ = JobStats();
-  {  // checkpoint / direction budget per buffer set: env or 56 GB (larger batches = fewer kernel
-     // tails: +2 % on cfg4 over 32 GB in a same-run A/B), capped by the device's memory
-    SEQALK_CUDA(cudaSetDevice(dev_));
-    size_t free_b = 0, total_b = 0;
-    SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    double budget_gb = 56.0;
-    if (const char *e = std::getenv("SEQALK_DIR_BUDGET_GB")) budget_gb = std::atof(e);
-    dir_budget_ = (size_t)(budget_gb * (double)(1ull << 30));
-    // our own (cached) direction buffers count as available
-    size_t own = 0;
-    for (const Slot &s : slots_) own += s.dirs.cap;
-    const size_t cap = (size_t)((double)(free_b + own) * 0.80 / nslots_);
-    if (dir_budget_ > cap) dir_budget_ = cap;
-  }
   // kernel variant
   variant_ = FillVariant();
   variant_.R = 16;  // measured best on B200 (profiles/): 16 rows per lane, cost table when possible
@@ -291,6 +277,23 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
       if (std::atoi(e) == 16) variant_.R = 16;
   }
   variant_.emit = !tiles_;
+  {  // checkpoint / direction budget per buffer set (larger batches = fewer kernel tails), capped
+     // by the device's memory.  dirs mode double-buffers the big arrays (fill of batch b+1 runs
+     // beside the traceback of batch b): 56 GB each; tile mode runs its stages back to back on
+     // one stream and needs a single set: 104 GB.
+    SEQALK_CUDA(cudaSetDevice(dev_));
+    size_t free_b = 0, total_b = 0;
+    SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const int nbig = tiles_ ? 1 : nslots_;
+    double budget_gb = tiles_ ? 104.0 : 56.0;
+    if (const char *e = std::getenv("SEQALK_DIR_BUDGET_GB")) budget_gb = std::atof(e);
+    dir_budget_ = (size_t)(budget_gb * (double)(1ull << 30));
+    // our own (cached) buffers count as available
+    size_t own = 0;
+    for (const Slot &s : slots_) own += s.dirs.cap + s.brow.cap;
+    const size_t cap = (size_t)((double)(free_b + own) * 0.80 / nbig);
+    if (dir_budget_ > cap) dir_budget_ = cap;
+  }
   mixed_ = tiles_;  // 512-row last strips where they halve the row padding
   if (const char *e = std::getenv("SEQALK_MIXED")) mixed_ = tiles_ && std::atoi(e) != 0;
   for (const TaskIJ &tk : tasks_)
@@ -455,16 +458,19 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   for (size_t b = batch_begin; b < batch_end; ++b) {
     const Batch &B = batches_[b];
     Slot &S = slots_[b % nslots_];
+    // tile mode: one stream, so one set of the big arrays serves every batch (the descriptor
+    // buffers stay per slot: the host fills the next batch's staging while this one runs)
+    Slot &G = tiles_ ? slots_[0] : S;
     // ---- size device buffers (for the largest batch of the job: at most one allocation)
     ensure(S.pairs, need_.count * sizeof(PairDesc));
     ensure(S.tasks, (size_t)need_.nstrips * sizeof(StripTask));
     ensure(S.slots, need_.count * sizeof(uint32_t));
     ensure(S.progress, (size_t)need_.nstrips * sizeof(uint32_t));
-    ensure(S.brow, need_.brow_ints * sizeof(int32_t));
-    ensure(S.dirs, need_.dir_bytes);
-    ensure(S.out, need_.out_bytes + BUFFER_SLACK);
-    ensure(S.align, need_.count * sizeof(PairAlign));
-    ensure(S.cost, need_.count * sizeof(int32_t));
+    ensure(G.brow, need_.brow_ints * sizeof(int32_t));
+    ensure(G.dirs, need_.dir_bytes);
+    ensure(G.out, need_.out_bytes + BUFFER_SLACK);
+    ensure(G.align, need_.count * sizeof(PairAlign));
+    ensure(G.cost, need_.count * sizeof(int32_t));
     ensure(S.counter, 2 * sizeof(uint32_t));
     // ---- build descriptors in pinned staging
     const size_t pairs_bytes = round_up(need_.count * sizeof(PairDesc), 256);
@@ -558,8 +564,8 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.ntasks = (uint32_t)n_main;
     fa.counter = static_cast<uint32_t *>(S.counter.p);
     fa.progress = static_cast<uint32_t *>(S.progress.p);
-    fa.brow = static_cast<int32_t *>(S.brow.p);
-    fa.dirs = static_cast<uint8_t *>(S.dirs.p);
+    fa.brow = static_cast<int32_t *>(G.brow.p);
+    fa.dirs = static_cast<uint8_t *>(G.dirs.p);
     fa.pxy = pxy_;
     fa.pgap = pgap_;
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 0], st));
@@ -588,9 +594,9 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.pairs = fa.pairs;
     ta.npairs = (uint32_t)B.count;
     ta.dirs = fa.dirs;
-    ta.out = static_cast<uint8_t *>(S.out.p);
-    ta.align = static_cast<PairAlign *>(S.align.p);
-    ta.path_cost = static_cast<int32_t *>(S.cost.p);
+    ta.out = static_cast<uint8_t *>(G.out.p);
+    ta.align = static_cast<PairAlign *>(G.align.p);
+    ta.path_cost = static_cast<int32_t *>(G.cost.p);
     ta.pxy = pxy_;
     ta.pgap = pgap_;
     ta.R = R;
@@ -726,15 +732,16 @@ bool DeviceWorker::fetch_alignment(size_t index_in_job, std::vector<uint8_t> &a1
   const Batch &B = batches_[b];
   if (index_in_job < B.first || index_in_job >= B.first + B.count) return false;
   Slot &S = slots_[b % nslots_];
+  Slot &G = tiles_ ? slots_[0] : S;
   size_t p = 0;
   while (p < S.last_pairs.size() && (size_t)S.last_pairs[p].task_id != index_in_job) ++p;
   if (p == S.last_pairs.size()) return false;
   const PairDesc &d = S.last_pairs[p];
   PairAlign al;
-  SEQALK_CUDA(cudaMemcpy(&al, static_cast<PairAlign *>(S.align.p) + p, sizeof al, cudaMemcpyDeviceToHost));
+  SEQALK_CUDA(cudaMemcpy(&al, static_cast<PairAlign *>(G.align.p) + p, sizeof al, cudaMemcpyDeviceToHost));
   a1.resize(al.len);
   a2.resize(al.len);
-  const uint8_t *out = static_cast<const uint8_t *>(S.out.p);
+  const uint8_t *out = static_cast<const uint8_t *>(G.out.p);
   if (al.len) {
     SEQALK_CUDA(cudaMemcpy(a1.data(), out + d.out_off + al.start, al.len, cudaMemcpyDeviceToHost));
     SEQALK_CUDA(cudaMemcpy(a2.data(), out + d.out_off + d.cap + al.start, al.len, cudaMemcpyDeviceToHost));

@@ -24,7 +24,7 @@
 //                          : min(H'[i-1][j-1] + pxy - 2*pgap, H'[i-1][j], H'[i][j-1])
 //     (comparisons are shift-invariant, so ties break exactly as in the reference);
 //   * tile mode (default, EMIT = false): scores only — per cell one IDP.4A (cost-table lookup
-//     + add, FMA pipe) and one VIMNMX3 (ALU pipe); the row of H' is kept every 256 DP rows and
+//     + add, FMA pipe) and one VIMNMX3 (ALU pipe); the row of H' is kept every TILE_ROWS (128) DP rows and
 //     each lane checkpoints its rows every 256 DP columns, from which traceback_tiles.cu
 //     recomputes directions for the tiles on the optimal path only;
 //   * directions mode (EMIT = true): per cell a 2-bit code is emitted: bit1 = "not diagonal",
@@ -56,11 +56,11 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 
 // EMIT = true : directions mode.  2-bit codes for every cell go to HBM (P.dir_off); the boundary
 //               row buffer holds one row per pair, rewritten in place strip after strip.
-// EMIT = false: tile mode.  Scores only; every 256 DP rows (lanes 7, 15, 23, 31 for R = 32) the
+// EMIT = false: tile mode.  Scores only; every TILE_ROWS = 128 DP rows (lanes 3, 7, ..., 31 for R = 32) the
 //               row of H' is kept (P.brow_off: R/8 rows per strip), and every CKQ macro columns each
 //               lane stores its R row values (P.dir_off reused as the checkpoint region:
 //               [checkpoint][padded row] int32).  The traceback recomputes directions only for
-//               the 256 x 4*CKQ tiles its path visits (traceback_tiles.cu).
+//               the TILE_ROWS x 4*CKQ tiles its path visits (traceback_tiles.cu).
 template <int R, int MODE, int ADDMODE, bool EMIT>
 __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc &P, const int s, const int row_base,
                                               const int lane) {
@@ -76,13 +76,13 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
   const uint8_t *__restrict__ seqbase = (MODE == MODE_TAB) ? a.codes : a.seq;
   const uint8_t *__restrict__ xs = seqbase + P.x_off;
   const unsigned *__restrict__ yw32 = reinterpret_cast<const unsigned *>(seqbase + P.y_off);
-  // boundary rows: in place (EMIT) or one row per 256 DP rows (tile mode, stride 4*nq+4 ints)
+  // boundary rows: in place (EMIT) or one row per TILE_ROWS DP rows (tile mode, stride 4*nq+4 ints)
   const uint64_t bstride = EMIT ? 0 : (uint64_t)(4 * nq + 4);
   int32_t *bbase = a.brow + P.brow_off;
   const int4 *__restrict__ brow_rd =
       reinterpret_cast<const int4 *>(EMIT ? bbase : bbase + (uint64_t)(first ? 0 : row_base / TILE_ROWS - 1) * bstride);
   int4 *__restrict__ brow_wr = reinterpret_cast<int4 *>(
-      EMIT ? bbase : bbase + (uint64_t)((row_base + lane * R) / TILE_ROWS) * bstride);  // kept row (DP row / 256) - 1
+      EMIT ? bbase : bbase + (uint64_t)((row_base + lane * R) / TILE_ROWS) * bstride);  // kept row (DP row / TILE_ROWS) - 1
   uint4 *__restrict__ dout =
       reinterpret_cast<uint4 *>(a.dirs + P.dir_off + (uint64_t)s * ((uint64_t)ngroups * 512ull)) + lane;
   const unsigned *prev_progress = a.progress + P.strip0 + (first ? 0 : s - 1);
@@ -180,8 +180,8 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
         if (EMIT) {
           if (lane == 31 && !last) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
         } else {
-          // every 256 rows (R = 16: lanes 15 and 31) keep the row for the tile traceback
-          if ((lane & (256 / R - 1)) == (256 / R - 1)) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
+          // every TILE_ROWS rows (R = 32: lanes 3, 7, ..., 31) keep the row for the tile traceback
+          if ((lane & (TILE_ROWS / R - 1)) == (TILE_ROWS / R - 1)) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
           // column checkpoint: H' of this lane's rows at the last column of macro col qc
           if (((qc + 1) & (CKQ - 1)) == 0) {
             int4 *dst = ck_wr + ((uint64_t)((qc + 1) / CKQ - 1) * mpad) / 4;

@@ -16,9 +16,12 @@ struct FillVariant {
   bool emit = true; // true: directions mode (2-bit codes to HBM); false: tile mode (scores +
                     // checkpoints, directions recomputed by the traceback for the tiles it visits)
 };
-// tile mode: a column checkpoint every CKQ macro columns (4*CKQ DP columns), a row every 256 rows
+// tile mode: a column checkpoint every CKQ macro columns (4*CKQ DP columns), a row every TILE_ROWS rows
 constexpr int CKQ = 64;
-constexpr int TILE_ROWS = 256;
+#ifndef SEQALK_TILE_ROWS
+#define SEQALK_TILE_ROWS 128
+#endif
+constexpr int TILE_ROWS = SEQALK_TILE_ROWS;  // 128 (default: -21 % traceback time on cfg4) or 256; 32 lanes x 4 or 8 rows in the recompute
 // bottom-row progress is published every 2^publish_shift macro columns (and at strip end):
 // 64 when a batch has plenty of independent pairs, 16 when consecutive strips of a few long
 // pairs must run as a tight wavefront (shorter start-up ramp)
@@ -46,7 +49,7 @@ struct FillArgs {
 struct TracebackArgs {
   const uint8_t *seq;
   const uint8_t *codes;     // letters remapped to 0..3 (tile mode with MODE_TAB), else null
-  const int32_t *brow;      // tile mode: kept boundary rows (one per 256 DP rows)
+  const int32_t *brow;      // tile mode: kept boundary rows (one per TILE_ROWS DP rows)
   int32_t mode;             // tile mode: MODE_* of the recompute (same arithmetic as the fill)
   int32_t addmode;          // tile mode: 2 = IDP.4A cost lookup in the recompute
   int32_t long_pairs;       // tile mode: 1 = four warps per pair (walk + look-ahead recompute)

@@ -1,13 +1,13 @@
 // traceback_tiles.cu — traceback for the tile mode: directions are NOT read from HBM but
-// recomputed, one 256-row x (4*CKQ)-column tile at a time, only for the tiles the optimal path
-// visits (about (m + n) / 256 of them), from the checkpoints the score-only fill left behind:
-// one row of H' every 256 DP rows and one column of H' every 4*CKQ DP columns.
+// recomputed, one TILE_ROWS-row x (4*CKQ)-column tile (128 x 256) at a time, only for the tiles the optimal path
+// visits (about m / 128 + n / 256 of them), from the checkpoints the score-only fill left behind:
+// one row of H' every TILE_ROWS DP rows and one column of H' every 4*CKQ DP columns.
 //
 // Same reference semantics as traceback.cu (submit/xuliny-seqalkway.cpp:502-558, :191-214):
 // the recompute runs the very same per-cell update as the fill (fill_core.cuh, EMIT = true), so
 // the 2-bit codes — and with them the tie-breaking — are identical to the directions mode.
 //
-// One warp per pair.  Per tile: lane t owns 8 rows, the warp sweeps the needed macro columns
+// One warp per pair.  Per tile: lane t owns RT rows, the warp sweeps the needed macro columns
 // as a skewed wavefront (exactly like the fill) writing the codes to shared memory, then walks
 // the path inside the tile until it leaves through the top or the left edge.
 #include "fill_core.cuh"
@@ -16,32 +16,16 @@ namespace seqalk {
 
 namespace {
 
-constexpr int RT = 8;  // rows per lane in the recompute: 32 lanes x 8 rows = TILE_ROWS
-static_assert(32 * RT == TILE_ROWS, "tile height");
+constexpr int RT = TILE_ROWS / 32;  // rows per lane in the recompute: 32 lanes x RT rows = TILE_ROWS
+constexpr int WPE = RT / 4;         // 32-bit words of direction codes per lane and macro column
+static_assert(RT == 8 || RT == 4, "tile height");
 
-// Right-to-left writer (32-bit words); every lane tracks the position, lane 0 stores.
-struct BackWriter0 {
-  uint8_t *base;
-  uint32_t pos;
-  uint32_t acc;
-  bool store;
-  __device__ __forceinline__ void init(uint8_t *b, uint32_t end, bool st) {
-    base = b;
-    pos = end;
-    acc = 0;
-    store = st;
-  }
-  __device__ __forceinline__ void put(uint32_t ch) {
-    --pos;
-    acc |= ch << (8 * (pos & 3));
-    if ((pos & 3) == 0) {
-      if (store) *reinterpret_cast<uint32_t *>(base + pos) = acc;
-      acc = 0;
-    }
-  }
-  __device__ __forceinline__ void finish() {
-    if ((pos & 3) && store) *reinterpret_cast<uint32_t *>(base + (pos & ~3u)) = acc;
-  }
+// Right-to-left output of the two alignment strings.  Every lane of the walking warp carries
+// the same position; the characters of 32 consecutive steps are stored by 32 lanes at once.
+struct PathOut {
+  uint8_t *o1, *o2;  // first character of each string's buffer
+  int pos;           // characters [pos, m + n) are written
+  int cost;          // this lane's share of the path cost
 };
 
 }  // namespace
@@ -78,17 +62,17 @@ __device__ __forceinline__ TileCtx make_ctx(const TracebackArgs &a, const PairDe
 }
 
 // Shared-memory image of one tile: direction codes [CKQ][32] + the tile's characters.
-constexpr int TILE_SMEM_BYTES = CKQ * 32 * (int)sizeof(uint2) + 2 * TILE_ROWS;
+constexpr int TILE_DIR_BYTES = CKQ * 32 * 4 * WPE;
+constexpr int TILE_SMEM_BYTES = TILE_DIR_BYTES + TILE_ROWS + 4 * CKQ;
 
 // Recomputes the directions of tile (hs, cb), macro columns [0, tq) and lanes [0, tmax], into
-// `tile` (one warp).  Same sweep as the fill: lane t owns 8 rows, trails lane t-1 by one macro
+// `tile` (one warp).  Same sweep as the fill: lane t owns RT rows, trails lane t-1 by one macro
 // column; left edge = column checkpoint cb-1, top edge = kept row hs-1.
 template <int MODE, int ADDMODE>
 __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb, int tq, int tmax, uint8_t *tile,
                                                int lane) {
   const unsigned FULL = 0xffffffffu;
-  uint2 *sdirs = reinterpret_cast<uint2 *>(tile);
-  uint64_t *schars = reinterpret_cast<uint64_t *>(sdirs + CKQ * 32);
+  uint32_t *sdirs = reinterpret_cast<uint32_t *>(tile);
   const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ, q0 = cb * CKQ;
   int xc[RT], h[RT];
   {
@@ -101,18 +85,27 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
     }
     if (cb > 0) {  // left edge = column checkpoint cb-1
       const int4 *src = reinterpret_cast<const int4 *>(T.ck + (uint64_t)(cb - 1) * T.mpad + (uint64_t)r0);
-      const int4 v0 = __ldcg(src), v1 = __ldcg(src + 1);
-      h[0] = v0.x; h[1] = v0.y; h[2] = v0.z; h[3] = v0.w;
-      h[4] = v1.x; h[5] = v1.y; h[6] = v1.z; h[7] = v1.w;
+#pragma unroll
+      for (int r4 = 0; r4 < RT / 4; ++r4) {
+        const int4 v = __ldcg(src + r4);
+        h[4 * r4] = v.x; h[4 * r4 + 1] = v.y; h[4 * r4 + 2] = v.z; h[4 * r4 + 3] = v.w;
+      }
     } else {
 #pragma unroll
       for (int r = 0; r < RT; ++r) h[r] = 0;
     }
   }
-  {  // stage the tile's characters (8 per lane; rows / columns past the ends are never walked)
-    const int r0 = row0 + lane * 8, c0 = col0 + lane * 8;
-    schars[lane] = r0 < T.m ? *reinterpret_cast<const uint64_t *>(T.xs + r0) : 0ull;
-    schars[32 + lane] = c0 < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + c0) : 0ull;
+  {  // stage the tile's characters (rows / columns past the ends are never walked)
+    static_assert(4 * CKQ == 256, "8 y characters per lane");
+    const int r0 = row0 + lane * RT, c0 = col0 + lane * 8;
+    if (RT == 8)
+      reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES)[lane] =
+          r0 < T.m ? *reinterpret_cast<const uint64_t *>(T.xs + r0) : 0ull;
+    else
+      reinterpret_cast<uint32_t *>(tile + TILE_DIR_BYTES)[lane] =
+          r0 < T.m ? *reinterpret_cast<const uint32_t *>(T.xs + r0) : 0u;
+    reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES + TILE_ROWS)[lane] =
+        c0 < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + c0) : 0ull;
   }
   const int32_t *toprow = hs > 0 ? T.brow + (uint64_t)(hs - 1) * T.bstride : nullptr;
   int dg = __shfl_up_sync(FULL, h[RT - 1], 1);
@@ -147,68 +140,80 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
       yw = ny;
       unsigned bits[RT / 4];
       macro_step<RT, MODE, ADDMODE, true>(h, dg, xc, up_in, yw, T.A, T.B, 1, -1, outv, bits);
-      sdirs[qc * 32 + lane] = make_uint2(bits[0], bits[1]);
+      if (RT == 8)
+        reinterpret_cast<uint2 *>(sdirs)[qc * 32 + lane] = make_uint2(bits[0], bits[WPE - 1]);
+      else
+        sdirs[qc * 32 + lane] = bits[0];
     }
   }
 }
 
 // Walks the path inside a recomputed tile from (i, j) until it leaves through the top or the
-// left edge (every lane walks; the writers store from lane 0 only).
-__device__ __forceinline__ void walk_tile(const uint8_t *tile, int row0, int col0, int &i, int &j, int &cost,
-                                          BackWriter0 &w1, BackWriter0 &w2, int pxy, int pgap) {
+// left edge.  All lanes follow the walk (it is one dependent chain of shared-memory lookups);
+// lane L keeps the cell and code of steps L, L + 32, ... and every 32 steps the warp emits the
+// characters and costs of those steps together.
+__device__ __forceinline__ void walk_tile(const uint8_t *tile, int row0, int col0, int &i, int &j, PathOut &W,
+                                          int pxy, int pgap, int lane) {
   const uint32_t *sdirs32 = reinterpret_cast<const uint32_t *>(tile);
-  const uint8_t *sxb = tile + CKQ * 32 * sizeof(uint2);
+  const uint8_t *sxb = tile + TILE_DIR_BYTES;
   const uint8_t *syb = sxb + TILE_ROWS;
   int li = i - 1 - row0, lj = j - 1 - col0;
-  while (li >= 0 && lj >= 0) {
-    const unsigned t = (unsigned)li >> 3, r = (unsigned)li & 7u, qc = (unsigned)lj >> 2, c = (unsigned)lj & 3u;
-    const unsigned idx = c * RT + r;
-    const uint32_t word = sdirs32[(qc * 32 + t) * 2 + (idx >> 4)];
-    const uint32_t code = (word >> (30 - 2 * (idx & 15u))) & 3u;
-    const uint32_t xch = sxb[li], ych = syb[lj];
-    if (!(code & DIR_NOT_DIAG)) {
-      w1.put(xch);
-      w2.put(ych);
-      cost += (xch == ych) ? 0 : pxy;
-      --li;
-      --lj;
-    } else if (!(code & DIR_LEFT_BETTER)) {
-      w1.put(xch);
-      w2.put('_');
-      cost += pgap;
-      --li;
-    } else {
-      w1.put('_');
-      w2.put(ych);
-      cost += pgap;
-      --lj;
+  int k = 0, my_li = 0, my_lj = 0;
+  uint32_t my_code = 0;
+  auto emit = [&](int base, int count) {  // steps [base, base + count), count <= 32
+    if (lane < count) {
+      const bool dx = my_code != (DIR_NOT_DIAG | DIR_LEFT_BETTER);  // consumes a character of x
+      const bool dy = my_code != DIR_NOT_DIAG;                      // consumes a character of y
+      const uint32_t xch = sxb[my_li], ych = syb[my_lj];
+      const int at = W.pos - 1 - (base + lane);
+      W.o1[at] = (uint8_t)(dx ? xch : (uint32_t)'_');
+      W.o2[at] = (uint8_t)(dy ? ych : (uint32_t)'_');
+      W.cost += (dx && dy) ? (xch == ych ? 0 : pxy) : pgap;
     }
+  };
+  while (li >= 0 && lj >= 0) {
+    const unsigned t = (unsigned)li / RT, r = (unsigned)li % RT, qc = (unsigned)lj >> 2, c = (unsigned)lj & 3u;
+    const unsigned idx = c * RT + r;
+    const uint32_t word = sdirs32[(qc * 32 + t) * WPE + (idx >> 4)];
+    const uint32_t code = (word >> (30 - 2 * (idx & 15u))) & 3u;  // 0, 1: diagonal; 2: up; 3: left
+    if ((k & 31) == lane) {
+      my_li = li;
+      my_lj = lj;
+      my_code = code;
+    }
+    li -= (code != (DIR_NOT_DIAG | DIR_LEFT_BETTER));
+    lj -= (code != DIR_NOT_DIAG);
+    ++k;
+    if ((k & 31) == 0) emit(k - 32, 32);
   }
+  if (k & 31) emit(k & ~31, k & 31);
+  W.pos -= k;
   i = row0 + li + 1;
   j = col0 + lj + 1;
 }
 
-// Tails (only one of i, j is non-zero) and the per-pair result record.
+// Tails (only one of i, j is non-zero) and the per-pair result record (one warp).
 __device__ __forceinline__ void finish_pair(const TracebackArgs &a, const TileCtx &T, uint32_t p, int i, int j,
-                                            int cost, BackWriter0 &w1, BackWriter0 &w2, bool writer) {
-  cost += (i + j) * a.pgap;
-  for (; i > 0; --i) {
-    w1.put(T.xs[i - 1]);
-    w2.put('_');
+                                            PathOut &W, int lane) {
+  for (int t = lane; t < i; t += 32) {
+    W.o1[W.pos - 1 - t] = T.xs[i - 1 - t];
+    W.o2[W.pos - 1 - t] = '_';
   }
-  for (; j > 0; --j) {
-    w1.put('_');
-    w2.put(T.ys[j - 1]);
+  W.pos -= i;
+  for (int t = lane; t < j; t += 32) {
+    W.o1[W.pos - 1 - t] = '_';
+    W.o2[W.pos - 1 - t] = T.ys[j - 1 - t];
   }
-  const uint32_t start = w1.pos;
-  w1.finish();
-  w2.finish();
-  if (writer) {
+  W.pos -= j;
+  int cost = W.cost;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, d);
+  if (lane == 0) {
     PairAlign res;
-    res.start = start;
-    res.len = (uint32_t)(T.m + T.n) - start;
+    res.start = (uint32_t)W.pos;
+    res.len = (uint32_t)(T.m + T.n - W.pos);
     a.align[p] = res;
-    a.path_cost[p] = cost;
+    a.path_cost[p] = cost + (i + j) * a.pgap;
   }
 }
 
@@ -221,10 +226,8 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
   const uint32_t p = blockIdx.x;
   const PairDesc P = a.pairs[p];
   const TileCtx T = make_ctx<MODE>(a, P);
-  BackWriter0 w1, w2;
-  w1.init(a.out + P.out_off, (uint32_t)(T.m + T.n), lane == 0);
-  w2.init(a.out + P.out_off + P.cap, (uint32_t)(T.m + T.n), lane == 0);
-  int i = T.m, j = T.n, cost = 0;
+  PathOut W{a.out + P.out_off, a.out + P.out_off + P.cap, T.m + T.n, 0};
+  int i = T.m, j = T.n;
   while (i > 0 && j > 0) {
     const int hs = (i - 1) / TILE_ROWS, cb = (j - 1) / (4 * CKQ);
     const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ;
@@ -232,10 +235,10 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
     const int tmax = (i - 1 - row0) / RT;      // last lane needed
     recompute_tile<MODE, ADDMODE>(T, hs, cb, tq, tmax, smem, lane);
     __syncwarp();
-    walk_tile(smem, row0, col0, i, j, cost, w1, w2, a.pxy, a.pgap);
+    walk_tile(smem, row0, col0, i, j, W, a.pxy, a.pgap, lane);
     __syncwarp();
   }
-  finish_pair(a, T, p, i, j, cost, w1, w2, lane == 0);
+  finish_pair(a, T, p, i, j, W, lane);
 }
 
 // Four warps per pair (jobs of a few long pairs, where one warp per pair leaves the GPU idle and
@@ -252,10 +255,7 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
   const uint32_t p = blockIdx.x;
   const PairDesc P = a.pairs[p];
   const TileCtx T = make_ctx<MODE>(a, P);
-  BackWriter0 w1, w2;
-  w1.init(a.out + P.out_off, (uint32_t)(T.m + T.n), threadIdx.x == 0);
-  w2.init(a.out + P.out_off + P.cap, (uint32_t)(T.m + T.n), threadIdx.x == 0);
-  int cost = 0;
+  PathOut W{a.out + P.out_off, a.out + P.out_off + P.cap, T.m + T.n, 0};
   if (threadIdx.x == 0) {
     s_i = T.m;
     s_j = T.n;
@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
     __syncthreads();  // everybody has read the tags before they change
     if (warp == 0) {
       int wi = i, wj = j;
-      walk_tile(smem + (size_t)cur * TILE_SMEM_BYTES, hs * TILE_ROWS, cb * 4 * CKQ, wi, wj, cost, w1, w2, a.pxy,
-                a.pgap);
+      walk_tile(smem + (size_t)cur * TILE_SMEM_BYTES, hs * TILE_ROWS, cb * 4 * CKQ, wi, wj, W, a.pxy, a.pgap,
+                lane);
       if (lane == 0) {
         s_i = wi;
         s_j = wj;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
     }
     __syncthreads();
   }
-  if (warp == 0) finish_pair(a, T, p, s_i, s_j, cost, w1, w2, lane == 0);
+  if (warp == 0) finish_pair(a, T, p, s_i, s_j, W, lane);
 }
 
 template <int MODE, int ADDMODE>
