@@ -17,7 +17,10 @@ struct FillVariant {
                     // checkpoints, directions recomputed by the traceback for the tiles it visits)
 };
 // tile mode: a column checkpoint every CKQ macro columns (4*CKQ DP columns), a row every TILE_ROWS rows
-constexpr int CKQ = 64;
+#ifndef SEQALK_CKQ
+#define SEQALK_CKQ 64
+#endif
+constexpr int CKQ = SEQALK_CKQ;  // 64 or 32
 #ifndef SEQALK_TILE_ROWS
 #define SEQALK_TILE_ROWS 128
 #endif

@@ -96,16 +96,20 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
     }
   }
   {  // stage the tile's characters (rows / columns past the ends are never walked)
-    static_assert(4 * CKQ == 256, "8 y characters per lane");
-    const int r0 = row0 + lane * RT, c0 = col0 + lane * 8;
+    static_assert(CKQ == 64 || CKQ == 32, "8 or 4 y characters per lane");
+    const int r0 = row0 + lane * RT, c0 = col0 + lane * (CKQ / 8);
     if (RT == 8)
       reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES)[lane] =
           r0 < T.m ? *reinterpret_cast<const uint64_t *>(T.xs + r0) : 0ull;
     else
       reinterpret_cast<uint32_t *>(tile + TILE_DIR_BYTES)[lane] =
           r0 < T.m ? *reinterpret_cast<const uint32_t *>(T.xs + r0) : 0u;
-    reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES + TILE_ROWS)[lane] =
-        c0 < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + c0) : 0ull;
+    if (CKQ == 64)
+      reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES + TILE_ROWS)[lane] =
+          c0 < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + c0) : 0ull;
+    else
+      reinterpret_cast<uint32_t *>(tile + TILE_DIR_BYTES + TILE_ROWS)[lane] =
+          c0 < T.n ? *reinterpret_cast<const uint32_t *>(T.ys + c0) : 0u;
   }
   const int32_t *toprow = hs > 0 ? T.brow + (uint64_t)(hs - 1) * T.bstride : nullptr;
   int dg = __shfl_up_sync(FULL, h[RT - 1], 1);
@@ -148,46 +152,68 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
   }
 }
 
+// Emits the steps recorded in `hist` (a sentinel 1 followed by one 2-bit code per step, oldest
+// first; at most 15 steps), the walk having been at tile cell (hli, hlj) before the first of
+// them: lane s rebuilds the cell of step s from the codes before it (x is consumed by every
+// step that is not LEFT, y by every step that is not UP) and stores its two characters.
+__device__ __forceinline__ void emit_steps(const uint8_t *sxb, const uint8_t *syb, uint32_t hist, int hli, int hlj,
+                                           PathOut &W, int pxy, int pgap, int lane) {
+  const int n = (31 - __clz(hist)) >> 1;
+  if (lane < n) {
+    const int sh = 2 * (n - 1 - lane);
+    const uint32_t code = (hist >> sh) & 3u;  // 0, 1: diagonal; 2: up; 3: left
+    const uint32_t hi = (hist >> 1) & 0x55555555u, lo = hist & 0x55555555u;
+    const uint32_t prior = 0xFFFFFFFCu << sh;  // the steps before this one
+    const int li = hli - (lane - __popc(hi & lo & prior)), lj = hlj - (lane - __popc(hi & ~lo & prior));
+    const bool dx = code != (DIR_NOT_DIAG | DIR_LEFT_BETTER), dy = code != DIR_NOT_DIAG;
+    const uint32_t xch = sxb[li], ych = syb[lj];
+    const int at = W.pos - 1 - lane;
+    W.o1[at] = (uint8_t)(dx ? xch : (uint32_t)'_');
+    W.o2[at] = (uint8_t)(dy ? ych : (uint32_t)'_');
+    W.cost += (dx && dy) ? (xch == ych ? 0 : pxy) : pgap;
+  }
+  W.pos -= n;
+}
+
 // Walks the path inside a recomputed tile from (i, j) until it leaves through the top or the
-// left edge.  All lanes follow the walk (it is one dependent chain of shared-memory lookups);
-// lane L keeps the cell and code of steps L, L + 32, ... and every 32 steps the warp emits the
-// characters and costs of those steps together.
+// left edge.  Every lane follows the walk.  One shared-memory word holds the 16 codes of an
+// RT x (16 / RT) block of cells; while the path stays inside the block the word is kept rotated
+// so that the current cell's code sits in the top two bits (a step is: read the code, rotate by
+// a table look-up, move, append the code to the history).  The history is emitted by up to 15
+// lanes at once (emit_steps).
 __device__ __forceinline__ void walk_tile(const uint8_t *tile, int row0, int col0, int &i, int &j, PathOut &W,
                                           int pxy, int pgap, int lane) {
+  constexpr int CW = 16 / RT;         // columns of a word's block
+  constexpr int MAXB = RT + CW - 1;   // most steps inside one block
+  // rotate amounts (2 bits per cell, cell index = column * RT + row) by code
+  constexpr uint32_t ROT = (2u * (RT + 1)) | (2u * (RT + 1)) << 8 | 2u << 16 | (2u * RT) << 24;
   const uint32_t *sdirs32 = reinterpret_cast<const uint32_t *>(tile);
   const uint8_t *sxb = tile + TILE_DIR_BYTES;
   const uint8_t *syb = sxb + TILE_ROWS;
   int li = i - 1 - row0, lj = j - 1 - col0;
-  int k = 0, my_li = 0, my_lj = 0;
-  uint32_t my_code = 0;
-  auto emit = [&](int base, int count) {  // steps [base, base + count), count <= 32
-    if (lane < count) {
-      const bool dx = my_code != (DIR_NOT_DIAG | DIR_LEFT_BETTER);  // consumes a character of x
-      const bool dy = my_code != DIR_NOT_DIAG;                      // consumes a character of y
-      const uint32_t xch = sxb[my_li], ych = syb[my_lj];
-      const int at = W.pos - 1 - (base + lane);
-      W.o1[at] = (uint8_t)(dx ? xch : (uint32_t)'_');
-      W.o2[at] = (uint8_t)(dy ? ych : (uint32_t)'_');
-      W.cost += (dx && dy) ? (xch == ych ? 0 : pxy) : pgap;
-    }
-  };
+  uint32_t hist = 1u;
+  int hli = li, hlj = lj;
   while (li >= 0 && lj >= 0) {
-    const unsigned t = (unsigned)li / RT, r = (unsigned)li % RT, qc = (unsigned)lj >> 2, c = (unsigned)lj & 3u;
-    const unsigned idx = c * RT + r;
-    const uint32_t word = sdirs32[(qc * 32 + t) * WPE + (idx >> 4)];
-    const uint32_t code = (word >> (30 - 2 * (idx & 15u))) & 3u;  // 0, 1: diagonal; 2: up; 3: left
-    if ((k & 31) == lane) {
-      my_li = li;
-      my_lj = lj;
-      my_code = code;
+    if (hist >= (1u << (2 * (16 - MAXB)))) {  // the next block might not fit
+      emit_steps(sxb, syb, hist, hli, hlj, W, pxy, pgap, lane);
+      hist = 1u;
+      hli = li;
+      hlj = lj;
     }
-    li -= (code != (DIR_NOT_DIAG | DIR_LEFT_BETTER));
-    lj -= (code != DIR_NOT_DIAG);
-    ++k;
-    if ((k & 31) == 0) emit(k - 32, 32);
+    const int bl = li & ~(RT - 1), bj = lj & ~(CW - 1);
+    const unsigned idx = (unsigned)(lj & (CW - 1)) * RT + (unsigned)(li & (RT - 1));
+    const uint32_t word = sdirs32[(((unsigned)lj >> 2) * 32 + (unsigned)li / RT) * WPE + ((unsigned)(lj & 3) / CW)];
+    uint32_t w = __funnelshift_l(word, word, 2 * idx);
+#pragma unroll 2
+    do {
+      const uint32_t code = w >> 30;
+      w = __funnelshift_r(w, w, __byte_perm(ROT, 0u, code));  // shift amount is taken mod 32
+      li -= (code != (DIR_NOT_DIAG | DIR_LEFT_BETTER));
+      lj -= (code != DIR_NOT_DIAG);
+      hist = hist * 4u + code;
+    } while ((((li ^ bl) & ~(RT - 1)) | ((lj ^ bj) & ~(CW - 1))) == 0);
   }
-  if (k & 31) emit(k & ~31, k & 31);
-  W.pos -= k;
+  if (hist > 1u) emit_steps(sxb, syb, hist, hli, hlj, W, pxy, pgap, lane);
   i = row0 + li + 1;
   j = col0 + lj + 1;
 }
