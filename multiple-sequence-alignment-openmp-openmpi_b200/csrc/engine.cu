@@ -334,7 +334,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     const uint64_t brow_ints = tiles_ ? (uint64_t)(geo.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(n) + 4)
                                       : 4ull * (uint64_t)macro_cols(n) + 4;
     // directions, or (tile mode) the column checkpoints [nq / CKQ][rows padded to the strips]
-    const uint64_t db = tiles_ ? (uint64_t)(macro_cols(n) / CKQ) * geo.mpad * 4 + 16
+    const uint64_t db = tiles_ ? (uint64_t)(macro_cols(n) / CKQ) * geo.mpad * 4 + 32
                                : (uint64_t)ns * strip_dir_bytes(n, R);
     // what counts against the budget: directions, or (tile mode) checkpoints + kept rows
     const uint64_t bb = tiles_ ? db + brow_ints * 4 : db;
@@ -517,7 +517,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       hp[p] = d;
       hs[p] = result_slots_.empty() ? (uint32_t)t_index : result_slots_[t_index];
       if (tiles_) {
-        dir_off += round_up((uint64_t)(macro_cols(d.n) / CKQ) * d.mpad * 4, 16);
+        dir_off += round_up((uint64_t)(macro_cols(d.n) / CKQ) * d.mpad * 4, 32);  // 256-bit checkpoint stores
         brow_off += (uint64_t)(d.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(d.n) + 4);
       } else {
         dir_off += (uint64_t)d.nstrips * strip_dir_bytes(d.n, R);

@@ -184,10 +184,15 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
           if ((lane & (TILE_ROWS / R - 1)) == (TILE_ROWS / R - 1)) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
           // column checkpoint: H' of this lane's rows at the last column of macro col qc
           if (((qc + 1) & (CKQ - 1)) == 0) {
+            // 256-bit stores (STG.E.256, sm_100): the branch is taken by one lane at a time, so
+            // every instruction in it costs the whole warp an issue slot
             int4 *dst = ck_wr + ((uint64_t)((qc + 1) / CKQ - 1) * mpad) / 4;
 #pragma unroll
-            for (int r4 = 0; r4 < R / 4; ++r4)
-              dst[r4] = make_int4(h[4 * r4], h[4 * r4 + 1], h[4 * r4 + 2], h[4 * r4 + 3]);
+            for (int r8 = 0; r8 < R / 8; ++r8)
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 2 * r8), "r"(h[8 * r8]),
+                           "r"(h[8 * r8 + 1]), "r"(h[8 * r8 + 2]), "r"(h[8 * r8 + 3]), "r"(h[8 * r8 + 4]),
+                           "r"(h[8 * r8 + 5]), "r"(h[8 * r8 + 6]), "r"(h[8 * r8 + 7])
+                           : "memory");
           }
         }
       }
@@ -237,9 +242,12 @@ static FillKernelPtr pick_kernel(const FillVariant &v) {
     if (v.mode == MODE_GENERAL) return fill_kernel<32, MODE_GENERAL, 0, false>;
     if (v.mode == MODE_CMP) return fill_kernel<32, MODE_CMP, 0, false>;
     if (v.mode == MODE_TAB && v.addmode == 2) {
+      // left alone ptxas takes 168 registers (3 CTAs per SM); capped at 128 (4 CTAs, 8 bytes of
+      // spill outside the loop) the fill is 0.8 % faster (same-box A/B, cfg3 and cfg4)
+      if (v.minb == 1) return fill_kernel<32, MODE_TAB, 2, false>;
       if (v.minb == 5) return fill_kernel<32, MODE_TAB, 2, false, 5>;
       if (v.minb == 6) return fill_kernel<32, MODE_TAB, 2, false, 6>;
-      return fill_kernel<32, MODE_TAB, 2, false>;
+      return fill_kernel<32, MODE_TAB, 2, false, 4>;
     }
     if (v.mode == MODE_TAB) return fill_kernel<32, MODE_TAB, 0, false>;
     return nullptr;

@@ -61,14 +61,23 @@ __device__ __forceinline__ TileCtx make_ctx(const TracebackArgs &a, const PairDe
   return T;
 }
 
-// Shared-memory image of one tile: direction codes [CKQ][32] + the tile's characters.
+// Shared-memory image of one tile: direction codes [CKQ][32] + the tile's characters, and
+// (STAGE) the tile's top edge: per macro column the 4 values of the kept row + the y word.
 constexpr int TILE_DIR_BYTES = CKQ * 32 * 4 * WPE;
-constexpr int TILE_SMEM_BYTES = TILE_DIR_BYTES + TILE_ROWS + 4 * CKQ;
+constexpr int TILE_CHAR_BYTES = TILE_ROWS + 4 * CKQ;
+constexpr int TILE_EDGE_BYTES = CKQ * 20;
+constexpr int tile_smem_bytes(bool stage) { return TILE_DIR_BYTES + TILE_CHAR_BYTES + (stage ? TILE_EDGE_BYTES : 0); }
+#ifndef SEQALK_TB_STAGE
+#define SEQALK_TB_STAGE 1
+#endif
 
 // Recomputes the directions of tile (hs, cb), macro columns [0, tq) and lanes [0, tmax], into
 // `tile` (one warp).  Same sweep as the fill: lane t owns RT rows, trails lane t-1 by one macro
 // column; left edge = column checkpoint cb-1, top edge = kept row hs-1.
-template <int MODE, int ADDMODE>
+// STAGE: the warp first copies the top edge to shared memory with a few wide loads; otherwise
+// lane 0 fetches it from global memory one macro column ahead, which exposes the load latency on
+// every step unless other warps cover it.
+template <int MODE, int ADDMODE, bool STAGE>
 __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb, int tq, int tmax, uint8_t *tile,
                                                int lane) {
   const unsigned FULL = 0xffffffffu;
@@ -119,7 +128,15 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
   int4 top = make_int4(0, 0, 0, 0);
   unsigned ynext = 0;
   const int4 *top4 = toprow ? reinterpret_cast<const int4 *>(toprow) + q0 : nullptr;
-  if (lane == 0) {
+  int4 *stop = reinterpret_cast<int4 *>(tile + TILE_DIR_BYTES + TILE_CHAR_BYTES);
+  unsigned *sy = reinterpret_cast<unsigned *>(stop + CKQ);
+  if (STAGE) {
+    for (int q = lane; q < tq; q += 32) {
+      stop[q] = top4 ? __ldcg(top4 + q) : make_int4(0, 0, 0, 0);
+      sy[q] = __ldg(T.yw32 + q0 + q);
+    }
+    __syncwarp();
+  } else if (lane == 0) {
     ynext = __ldg(T.yw32 + q0);
     if (top4) top = __ldcg(top4);
   }
@@ -131,10 +148,15 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
     up_in[2] = __shfl_up_sync(FULL, outv[2], 1);
     up_in[3] = __shfl_up_sync(FULL, outv[3], 1);
     unsigned ny = __shfl_up_sync(FULL, yw, 1);
+    if (STAGE) {
+      const int qs = min(q, tq - 1);  // broadcast reads; only lane 0 uses them, and only while q < tq
+      top = stop[qs];
+      ynext = sy[qs];
+    }
     if (lane == 0) {
       up_in[0] = top.x; up_in[1] = top.y; up_in[2] = top.z; up_in[3] = top.w;
       ny = ynext;
-      if (q + 1 < tq) {  // look-ahead for the next macro column
+      if (!STAGE && q + 1 < tq) {  // look-ahead for the next macro column
         ynext = __ldg(T.yw32 + q0 + q + 1);
         if (top4) top = __ldcg(top4 + q + 1);
       }
@@ -245,7 +267,7 @@ __device__ __forceinline__ void finish_pair(const TracebackArgs &a, const TileCt
 
 // One warp per pair (jobs with many pairs): recompute the part of the tile up-left of the entry
 // cell, walk it, repeat.
-template <int MODE, int ADDMODE>
+template <int MODE, int ADDMODE, bool STAGE>
 __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x;
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
     const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ;
     const int tq = ((j - 1 - col0) >> 2) + 1;  // macro columns needed
     const int tmax = (i - 1 - row0) / RT;      // last lane needed
-    recompute_tile<MODE, ADDMODE>(T, hs, cb, tq, tmax, smem, lane);
+    recompute_tile<MODE, ADDMODE, STAGE>(T, hs, cb, tq, tmax, smem, lane);
     __syncwarp();
     walk_tile(smem, row0, col0, i, j, W, a.pxy, a.pgap, lane);
     __syncwarp();
@@ -272,6 +294,7 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
 // in full — the up to three tiles the path can enter next (above, left, above-left), so the next
 // tile is already in shared memory when the walk leaves the current one.
 constexpr int LONG_SLOTS = 4;
+constexpr int LONG_TILE_BYTES = tile_smem_bytes(true);
 template <int MODE, int ADDMODE>
 __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const TracebackArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -294,7 +317,7 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
   {
     const int hs = (T.m - 1) / TILE_ROWS, cb = (T.n - 1) / (4 * CKQ);
     if (warp == 1) {
-      recompute_tile<MODE, ADDMODE>(T, hs, cb, full_tq(cb), full_tmax(hs), smem, lane);
+      recompute_tile<MODE, ADDMODE, true>(T, hs, cb, full_tq(cb), full_tmax(hs), smem, lane);
       if (lane == 0) {
         s_tag[0][0] = hs;
         s_tag[0][1] = cb;
@@ -339,7 +362,7 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
     __syncthreads();  // everybody has read the tags before they change
     if (warp == 0) {
       int wi = i, wj = j;
-      walk_tile(smem + (size_t)cur * TILE_SMEM_BYTES, hs * TILE_ROWS, cb * 4 * CKQ, wi, wj, W, a.pxy, a.pgap,
+      walk_tile(smem + (size_t)cur * LONG_TILE_BYTES, hs * TILE_ROWS, cb * 4 * CKQ, wi, wj, W, a.pxy, a.pgap,
                 lane);
       if (lane == 0) {
         s_i = wi;
@@ -348,8 +371,8 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
     } else {
       const int c = warp - 1;
       if (target[c] >= 0) {
-        recompute_tile<MODE, ADDMODE>(T, cand_hs[c], cand_cb[c], full_tq(cand_cb[c]), full_tmax(cand_hs[c]),
-                                      smem + (size_t)target[c] * TILE_SMEM_BYTES, lane);
+        recompute_tile<MODE, ADDMODE, true>(T, cand_hs[c], cand_cb[c], full_tq(cand_cb[c]), full_tmax(cand_hs[c]),
+                                            smem + (size_t)target[c] * LONG_TILE_BYTES, lane);
         if (lane == 0) {
           s_tag[target[c]][0] = cand_hs[c];
           s_tag[target[c]][1] = cand_cb[c];
@@ -364,13 +387,14 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
 template <int MODE, int ADDMODE>
 static cudaError_t launch_tiles(const TracebackArgs &args, cudaStream_t stream) {
   if (args.long_pairs) {
-    const size_t smem = (size_t)LONG_SLOTS * TILE_SMEM_BYTES;
+    const size_t smem = (size_t)LONG_SLOTS * LONG_TILE_BYTES;
     cudaError_t e = cudaFuncSetAttribute(traceback_tiles_long_kernel<MODE, ADDMODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     traceback_tiles_long_kernel<MODE, ADDMODE><<<args.npairs, 128, smem, stream>>>(args);
   } else {
-    traceback_tiles_kernel<MODE, ADDMODE><<<args.npairs, 32, TILE_SMEM_BYTES, stream>>>(args);
+    constexpr bool STAGE = SEQALK_TB_STAGE != 0;
+    traceback_tiles_kernel<MODE, ADDMODE, STAGE><<<args.npairs, 32, tile_smem_bytes(STAGE), stream>>>(args);
   }
   return cudaGetLastError();
 }
