@@ -427,8 +427,11 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     h_dig = static_cast<uint8_t *>(h_res_) + std::max<size_t>(T, 1) * 4;
     fold_hex[0] = 0;
   }
-  auto fold_ready = [&](bool wait) {
-    while (next_fold < batch_end) {
+  // Folds the batches below `limit` whose results have landed.  `limit` must not exceed the
+  // batches enqueued in THIS run: the events of later batches still carry their (completed)
+  // record of the previous run.
+  auto fold_ready = [&](bool wait, size_t limit) {
+    while (next_fold < limit) {
       cudaEvent_t done = ev_[EV * next_fold + 5];
       if (wait) {
         SEQALK_CUDA(cudaEventSynchronize(done));
@@ -644,12 +647,12 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
         }
         async_cv_.notify_all();
       }
-    if (streaming) fold_ready(false);  // fold what has landed while the GPU works on later batches
+    if (streaming) fold_ready(false, b + 1);  // fold what has landed while the GPU works on later batches
     stats_.fill_launches++;
     stats_.traceback_launches++;
     stats_.digest_launches++;
   }
-  if (streaming) fold_ready(true);
+  if (streaming) fold_ready(true, batch_end);
   SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
   SEQALK_CUDA(cudaStreamSynchronize(post_stream_));
   for (Slot &S : slots_) S.staged_pending = S.post_pending = false;

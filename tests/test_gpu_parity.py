@@ -5,6 +5,7 @@ import hashlib
 import os
 import random
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -176,6 +177,33 @@ def test_batching_does_not_change_results(seqalk, oracle, workloads, monkeypatch
     assert d1 == od and np.array_equal(p1, op)
 
 
+def test_streaming_fold_with_blocking_launches(oracle, workloads):
+    """The public call folds the chain batch by batch while later batches are still to be
+    enqueued.  With synchronous launches (CUDA_LAUNCH_BLOCKING=1, or a profiler) a batch is
+    finished by the time the host looks at it, so the fold catches up with the enqueue loop:
+    it must never look past the batches enqueued in this call (their events are unrecorded or
+    carry the previous call's record).  Fresh process: the variable is read at CUDA init."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import importlib, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "pkg = importlib.import_module('multiple-sequence-alignment-openmp-openmpi_b200')\n"
+        "w = importlib.import_module('multiple-sequence-alignment-openmp-openmpi_b200.workloads')\n"
+        "for seed in (5, 6):\n"
+        "    genes = w.mixed(14, seed=seed, lo=300, hi=2500)\n"
+        "    d, p = pkg.get_minimum_penalties(genes, 3, 2)\n"
+        "    print(d, ' '.join(str(int(x)) for x in p))\n" % root)
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", SEQALK_DIR_BUDGET_GB="0.0005")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert len(lines) == 2
+    for seed, line in zip((5, 6), lines):
+        od, op, _ = oracle.all_pairs(workloads.mixed(14, seed=seed, lo=300, hi=2500), 3, 2)
+        digest, pens = line.split(" ", 1)
+        assert digest == od and [int(x) for x in pens.split()] == [int(x) for x in op]
+
+
 def test_job_subset_and_device_pointers(seqalk, oracle, workloads):
     import torch
 
@@ -323,6 +351,22 @@ def test_two_gpus_in_process_match_one_gpu(seqalk, oracle, workloads):
         seqalk.init(1)
     assert d2 == od and np.array_equal(p2, op)
     assert d2b == od and np.array_equal(p2b, op)
+
+
+def test_two_gpus_in_process_chunked_fold(seqalk, oracle):
+    """79 800 pairs on two GPUs of one process: the job is cut into two chunks of task ids,
+    each balanced over the GPUs; the host folds chunk 0 while the GPUs run chunk 1."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rnd = random.Random(8)
+    genes = [bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(1, 40))) for _ in range(400)]
+    od, op, _ = oracle.all_pairs(genes, 3, 2)
+    try:
+        seqalk.init(2)
+        d2, p2 = seqalk.get_minimum_penalties(genes, 3, 2)
+    finally:
+        seqalk.init(1)
+    assert d2 == od and np.array_equal(p2, op)
 
 
 @pytest.mark.parametrize("mode", ["tiles", "dirs"])
