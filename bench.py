@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "multiple-sequence-alignment-openmp-openmpi_b200"
 OPS_PER_CELL = 10  # algorithmic int32 lane-ops per DP cell
-EXECUTED_PER_CELL = 2.67  # lane-instructions the tile-mode fill executes per cell (ncu, profiles/)
+EXECUTED_PER_CELL = 2.47  # lane-instructions the tile-mode fill executes per cell (ncu, profiles/)
 
 
 def parse_args():
@@ -315,7 +315,7 @@ def main():
                           "peak": peaks["lop3+imad"] / 1e9, "unit": "Ginstr/s",
                           "frac": (agg_ops_rate / world / OPS_PER_CELL * EXECUTED_PER_CELL) / peaks["lop3+imad"]
                           if tile_mode else None,
-                          "source": "profiles/r01_fill_tiles_cfg4_ncu_summary.txt"},
+                          "source": "profiles/r01_fill_tiles_cfg4_final_ncu_summary.txt"},
                 "fill_ms_per_step_max_rank": fill_ms_max,
                 "hbm": {"bound": "hbm", "achieved": agg_dir_rate / world / 1e9, "unit": "GB/s",
                         "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]

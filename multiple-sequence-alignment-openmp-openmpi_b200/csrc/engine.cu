@@ -358,6 +358,13 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     ++next_end;
   }
   stats_.batches = (uint32_t)batches_.size();
+  // one event per chunk, created here: wait_chunk() reads this vector from the caller's thread
+  // while the enqueue thread of start_async() is running
+  while (chunk_ev_.size() + 1 < chunk_batch_.size()) {
+    cudaEvent_t e;
+    SEQALK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    chunk_ev_.push_back(e);
+  }
   // fast path needs non-negative penalties and scores far from int32 overflow
   // (|H'| <= 2*max(pxy,pgap)*(m+n)); anything else takes the exact-select kernel.
   const int64_t pmax = std::max<int64_t>(std::max(pxy, pgap), 1);
@@ -635,11 +642,6 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     // chunk boundary: mark the chunk's results with an event and tell waiters
     for (size_t c = 0; c + 1 < chunk_batch_.size(); ++c)
       if (chunk_batch_[c + 1] == b + 1 && chunk_batch_[c + 1] > chunk_batch_[c]) {
-        while (chunk_ev_.size() <= c) {
-          cudaEvent_t e;
-          SEQALK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-          chunk_ev_.push_back(e);
-        }
         SEQALK_CUDA(cudaEventRecord(chunk_ev_[c], st));
         {
           std::lock_guard<std::mutex> g(async_mu_);
