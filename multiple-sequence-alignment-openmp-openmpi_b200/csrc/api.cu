@@ -192,25 +192,49 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
   partition_all_chunks(pack.len.data(), k, N, bounds, per);
   mark("partitioned");
   DeviceArray pen0(0, (size_t)T * sizeof(int32_t)), dig0(0, (size_t)T * 64);
+  {  // upload + plan on every GPU at once; nothing is started until all of them succeeded
+    std::vector<std::thread> th;
+    std::vector<std::string> errs((size_t)N);
+    for (int d = 0; d < N; ++d)
+      th.emplace_back([&, d]() {
+        try {
+          std::vector<TaskIJ> tasks;
+          std::vector<uint32_t> slots;
+          std::vector<size_t> ends;
+          for (int c = 0; c < nchunks; ++c) {
+            for (int64_t id : per[c][d]) {
+              TaskIJ t;
+              task_from_id(id, &t.i, &t.j);
+              tasks.push_back(t);
+              slots.push_back((uint32_t)id);
+            }
+            ends.push_back(tasks.size());
+          }
+          DeviceWorker &w = *r.workers[d];
+          w.load(pack);
+          w.plan(tasks, pxy, pgap, &slots, &ends);
+        } catch (const std::exception &e) {
+          errs[d] = e.what();
+          if (errs[d].empty()) errs[d] = "unknown error";
+        }
+      });
+    for (std::thread &t : th) t.join();
+    for (int d = 0; d < N; ++d)
+      if (!errs[d].empty()) throw std::runtime_error("GPU " + std::to_string(d) + ": " + errs[d]);
+  }
+  mark("loaded and planned");
   for (int d = 0; d < N; ++d) {
-    std::vector<TaskIJ> tasks;
-    std::vector<uint32_t> slots;
-    std::vector<size_t> ends;
-    for (int c = 0; c < nchunks; ++c) {
-      for (int64_t id : per[c][d]) {
-        TaskIJ t;
-        task_from_id(id, &t.i, &t.j);
-        tasks.push_back(t);
-        slots.push_back((uint32_t)id);
+    try {
+      r.workers[d]->start_async(static_cast<int32_t *>(pen0.p), static_cast<uint8_t *>(dig0.p));
+    } catch (...) {  // the GPUs already started write into pen0 / dig0: let them finish first
+      for (int e = 0; e < d; ++e) {
+        try {
+          r.workers[e]->finish_async();
+        } catch (...) {
+        }
       }
-      ends.push_back(tasks.size());
+      throw;
     }
-    DeviceWorker &w = *r.workers[d];
-    w.load(pack);
-    mark("loaded on GPU", d);
-    w.plan(tasks, pxy, pgap, &slots, &ends);
-    mark("planned on GPU", d);
-    w.start_async(static_cast<int32_t *>(pen0.p), static_cast<uint8_t *>(dig0.p));
   }
   std::vector<uint8_t> digests((size_t)T * 64);
   size_t hl = 0;
