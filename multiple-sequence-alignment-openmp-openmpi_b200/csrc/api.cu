@@ -62,6 +62,27 @@ struct Runtime {
   std::mutex mu;
   std::vector<std::unique_ptr<DeviceWorker>> workers;  // devices 0..n-1
   bool peer_ok = false;                                 // every worker can store into device 0
+  // fused gather: task-ordered result arrays on device 0, kept between calls (allocating and
+  // freeing peer-mapped memory inside the call cost up to 0.6 s on some boxes)
+  void *pen0 = nullptr, *dig0 = nullptr;
+  size_t res_cap = 0;  // tasks
+  void reserve_results(size_t tasks) {
+    if (tasks <= res_cap) return;
+    release_results();
+    SEQALK_CUDA(cudaSetDevice(0));
+    SEQALK_CUDA(cudaMalloc(&pen0, tasks * sizeof(int32_t)));
+    SEQALK_CUDA(cudaMalloc(&dig0, tasks * 64));
+    res_cap = tasks;
+  }
+  void release_results() {
+    if (pen0 || dig0) {
+      cudaSetDevice(0);
+      cudaFree(pen0);
+      cudaFree(dig0);
+    }
+    pen0 = dig0 = nullptr;
+    res_cap = 0;
+  }
 };
 Runtime &rt() {
   static Runtime r;
@@ -86,6 +107,7 @@ void init_locked(Runtime &r, int ngpus) {
         "no CUDA device visible: libseqalk has no CPU fallback (needs an sm_100a GPU)");
   }
   if (ngpus <= 0 || ngpus > visible) ngpus = visible;
+  r.release_results();
   for (auto &w : r.workers) pool().release(std::move(w));
   r.workers.clear();
   for (int d = 0; d < ngpus; ++d) r.workers.push_back(pool().acquire(d));
@@ -191,7 +213,9 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
   std::vector<std::vector<std::vector<int64_t>>> per;
   partition_all_chunks(pack.len.data(), k, N, bounds, per);
   mark("partitioned");
-  DeviceArray pen0(0, (size_t)T * sizeof(int32_t)), dig0(0, (size_t)T * 64);
+  r.reserve_results((size_t)T);
+  int32_t *const pen0 = static_cast<int32_t *>(r.pen0);
+  uint8_t *const dig0 = static_cast<uint8_t *>(r.dig0);
   {  // upload + plan on every GPU at once; nothing is started until all of them succeeded
     std::vector<std::thread> th;
     std::vector<std::string> errs((size_t)N);
@@ -225,7 +249,7 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
   mark("loaded and planned");
   for (int d = 0; d < N; ++d) {
     try {
-      r.workers[d]->start_async(static_cast<int32_t *>(pen0.p), static_cast<uint8_t *>(dig0.p));
+      r.workers[d]->start_async(pen0, dig0);
     } catch (...) {  // the GPUs already started write into pen0 / dig0: let them finish first
       for (int e = 0; e < d; ++e) {
         try {
@@ -250,10 +274,8 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
       const size_t lo = (size_t)bounds[c], n = (size_t)(bounds[c + 1] - bounds[c]);
       if (!n) continue;
       SEQALK_CUDA(cudaSetDevice(0));
-      SEQALK_CUDA(cudaMemcpy(penalties + lo, static_cast<int32_t *>(pen0.p) + lo, n * sizeof(int32_t),
-                             cudaMemcpyDeviceToHost));
-      SEQALK_CUDA(cudaMemcpy(digests.data() + 64 * lo, static_cast<uint8_t *>(dig0.p) + 64 * lo, n * 64,
-                             cudaMemcpyDeviceToHost));
+      SEQALK_CUDA(cudaMemcpy(penalties + lo, pen0 + lo, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      SEQALK_CUDA(cudaMemcpy(digests.data() + 64 * lo, dig0 + 64 * lo, n * 64, cudaMemcpyDeviceToHost));
       if (folder.joinable()) folder.join();
       mark("folding chunk", c);
       folder = std::thread([&, lo, n]() { fold_chain(digests.data() + 64 * lo, n, digest_hex, &hl); });
@@ -270,6 +292,7 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
       if (error.empty()) error = "GPU " + std::to_string(d) + ": " + e.what();
     }
   }
+  mark("GPUs idle");
   if (!error.empty()) throw std::runtime_error(error);
 }
 
@@ -397,6 +420,7 @@ int seqalk_init(int ngpus) {
 void seqalk_shutdown(void) {
   Runtime &r = rt();
   std::lock_guard<std::mutex> g(r.mu);
+  r.release_results();
   r.workers.clear();
   pool().clear();
 }
