@@ -280,7 +280,8 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   {  // checkpoint / direction budget per buffer set (larger batches = fewer kernel tails), capped
      // by the device's memory.  dirs mode double-buffers the big arrays (fill of batch b+1 runs
      // beside the traceback of batch b): 56 GB each; tile mode runs its stages back to back on
-     // one stream and needs a single set: 104 GB.
+     // one stream and needs a single set: 104 GB (136 GB: 18 instead of 24 batches on cfg4 and
+     // -0.6 % job time in a same-box A/B; not taken, to leave memory for the caller).
     SEQALK_CUDA(cudaSetDevice(dev_));
     size_t free_b = 0, total_b = 0;
     SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
