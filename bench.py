@@ -292,7 +292,7 @@ def main():
                        "pgap": pgap, "k": len(genes), "pairs": T, "cells": cells, "sharding": f"lpt-cells x{world}",
                        "gather_chunks": nchunks,
                        "traceback": "tiles (score-only fill + per-tile recompute)" if tile_mode else "dirs (2-bit directions in HBM)",
-                       "l2": "working set (packed directions, GBs per batch) far exceeds the 126 MB L2; no flush needed"},
+                       "l2": "working set (checkpoints / packed directions: tens of GB per batch, every step a new pass over them) far exceeds the 126 MB L2; no flush needed"},
             "clocks": clocks,
             "e2e": {"value": cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h},

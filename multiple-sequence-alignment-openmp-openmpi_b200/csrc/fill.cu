@@ -24,9 +24,9 @@
 //                          : min(H'[i-1][j-1] + pxy - 2*pgap, H'[i-1][j], H'[i][j-1])
 //     (comparisons are shift-invariant, so ties break exactly as in the reference);
 //   * tile mode (default, EMIT = false): scores only — per cell one IDP.4A (cost-table lookup
-//     + add, FMA pipe) and one VIMNMX3 (ALU pipe); the row of H' is kept every TILE_ROWS (128) DP rows and
-//     each lane checkpoints its rows every 256 DP columns, from which traceback_tiles.cu
-//     recomputes directions for the tiles on the optimal path only;
+//     + add, FMA pipe) and one VIMNMX3 (ALU pipe); the row of H' is kept every TILE_ROWS
+//     (128) DP rows and each lane checkpoints its rows every 256 DP columns, from which
+//     traceback_tiles.cu recomputes directions for the tiles on the optimal path only;
 //   * directions mode (EMIT = true): per cell a 2-bit code is emitted: bit1 = "not diagonal",
 //     bit0 = "left strictly better than up".  The traceback reads DIAG if !bit1, else LEFT if
 //     bit0, else UP — the reference's priority order (match, mismatch-diag, up, left;
