@@ -60,6 +60,15 @@ int seqalk_all_pairs(const char *const *seqs, const int32_t *lens, int32_t k, in
 int seqalk_pair(const char *x, int32_t m, const char *y, int32_t n, int32_t pxy, int32_t pgap,
                 int32_t *xans, int32_t *yans, int32_t *penalty_out);
 
+/* Score-only forms: the penalties dp[m][n] (submit/xuliny-seqalkway.cpp:560)
+ * without alignment strings or digest.  With <= 4 distinct letters in the input the DP fill alone
+ * produces them (no traceback, no hashing); other alphabets run fill + traceback and return the
+ * path cost.  The full entry points above cross-check the two on the device for every pair. */
+int seqalk_all_pairs_scores(const char *const *seqs, const int32_t *lens, int32_t k, int32_t pxy, int32_t pgap,
+                            int32_t *penalties_out);
+int seqalk_pair_score(const char *x, int32_t m, const char *y, int32_t n, int32_t pxy, int32_t pgap,
+                      int32_t *penalty_out);
+
 /* ---- sharded execution: one process per GPU ------------------------------------------- */
 
 /* T = k(k-1)/2 */
@@ -99,6 +108,7 @@ typedef struct seqalk_stats {
   double wall_ms;             /* host wall time of the last seqalk_job_run */
   uint32_t tile_mode;         /* 1: score-only fill + tile-recompute traceback, 0: directions in HBM */
   uint32_t fill_rows_per_lane;
+  uint32_t self_checked;      /* 1: every penalty was compared on the device with the fill's own dp[m][n] */
 } seqalk_stats_t;
 
 /* Creates a job on CUDA device `device`: copies the k sequences to the GPU and plans the
@@ -124,7 +134,9 @@ int seqalk_job_run_chunk(seqalk_job_t *job, int32_t chunk, void *penalties_dev, 
 int seqalk_job_start_async(seqalk_job_t *job, void *penalties_dev, void *digests_dev);
 int seqalk_job_wait_chunk(seqalk_job_t *job, int32_t chunk, void *consumer_stream);
 int seqalk_job_finish_async(seqalk_job_t *job);
-/* D2H of the job-owned results. */
+/* Score-only pass over the job's tasks (see seqalk_all_pairs_scores); penalties_dev NULL = job-owned. */
+int seqalk_job_run_scores(seqalk_job_t *job, void *penalties_dev);
+/* D2H of the job-owned results (fails if the last run wrote to caller-supplied device memory). */
 int seqalk_job_fetch(seqalk_job_t *job, int32_t *penalties_out, uint8_t *digests_out);
 int seqalk_job_stats(const seqalk_job_t *job, seqalk_stats_t *stats_out);
 void seqalk_job_destroy(seqalk_job_t *job);

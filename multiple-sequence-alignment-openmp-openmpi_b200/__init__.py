@@ -27,7 +27,7 @@ import numpy as np
 
 __all__ = [
     "SeqalkError", "lib", "library_path", "getMinimumPenalties", "getMinimumPenalty", "do_MPI_task",
-    "get_minimum_penalties", "get_minimum_penalty", "Job", "JobStats", "partition", "partition_all", "partition_chunks", "chunk_bounds", "task_ij",
+    "get_minimum_penalties", "get_minimum_penalty", "all_pairs_scores", "pair_score", "Job", "JobStats", "partition", "partition_all", "partition_chunks", "chunk_bounds", "task_ij",
     "num_tasks", "fold_chain", "sha512_hex", "init", "shutdown", "device_count", "version",
 ]
 
@@ -51,6 +51,7 @@ class _Stats(ctypes.Structure):
         ("digest_launches", ctypes.c_uint32), ("fill_ms", ctypes.c_double),
         ("traceback_ms", ctypes.c_double), ("digest_ms", ctypes.c_double), ("wall_ms", ctypes.c_double),
         ("tile_mode", ctypes.c_uint32), ("fill_rows_per_lane", ctypes.c_uint32),
+        ("self_checked", ctypes.c_uint32),
     ]
 
 
@@ -68,6 +69,8 @@ C_ABI = [
     ("seqalk_version", _c.c_char_p, []),
     ("seqalk_all_pairs", _c.c_int, [_c.POINTER(_c.c_void_p), _I32P, _c.c_int32, _c.c_int32, _c.c_int32, _I32P, _c.c_char_p]),
     ("seqalk_pair", _c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _I32P, _I32P, _I32P]),
+    ("seqalk_all_pairs_scores", _c.c_int, [_c.POINTER(_c.c_void_p), _I32P, _c.c_int32, _c.c_int32, _c.c_int32, _I32P]),
+    ("seqalk_pair_score", _c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _I32P]),
     ("seqalk_num_tasks", _c.c_int64, [_c.c_int32]),
     ("seqalk_task_ij", _c.c_int, [_c.c_int64, _I32P, _I32P]),
     ("seqalk_partition", _c.c_int, [_I32P, _c.c_int32, _c.c_int64, _c.c_int64, _c.c_int32, _c.c_int32, _I64P, _I64P]),
@@ -81,6 +84,7 @@ C_ABI = [
     ("seqalk_job_start_async", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
     ("seqalk_job_wait_chunk", _c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p]),
     ("seqalk_job_finish_async", _c.c_int, [_c.c_void_p]),
+    ("seqalk_job_run_scores", _c.c_int, [_c.c_void_p, _c.c_void_p]),
     ("seqalk_job_fetch", _c.c_int, [_c.c_void_p, _I32P, _U8P]),
     ("seqalk_job_stats", _c.c_int, [_c.c_void_p, _c.POINTER(_Stats)]),
     ("seqalk_job_destroy", None, [_c.c_void_p]),
@@ -180,6 +184,28 @@ def get_minimum_penalties(genes: Sequence, pxy: int, pgap: int) -> Tuple[str, np
     _check(lib().seqalk_all_pairs(a.ptrs, a.lens_p, a.k, int(pxy), int(pgap),
                                   penalties.ctypes.data_as(_I32P), digest))
     return digest.value.decode("ascii"), penalties[:T]
+
+
+def all_pairs_scores(genes: Sequence, pxy: int, pgap: int) -> np.ndarray:
+    """Score-only form: the penalties ``dp[m][n]`` of all pairs (task order) from the DP fill,
+    without alignment strings or digest (``seqalk_all_pairs_scores``)."""
+    a = _SeqArgs(genes)
+    T = a.k * (a.k - 1) // 2
+    penalties = np.zeros(max(T, 1), dtype=np.int32)
+    _check(lib().seqalk_all_pairs_scores(a.ptrs, a.lens_p, a.k, int(pxy), int(pgap),
+                                         penalties.ctypes.data_as(_I32P)))
+    return penalties[:T]
+
+
+def pair_score(x, y, pxy: int, pgap: int) -> int:
+    """Score-only form of one pair (``seqalk_pair_score``): ``dp[m][n]``."""
+    xb, yb = _as_bytes(x), _as_bytes(y)
+    pen = ctypes.c_int32(0)
+    xbuf = ctypes.create_string_buffer(xb, max(len(xb), 1))
+    ybuf = ctypes.create_string_buffer(yb, max(len(yb), 1))
+    _check(lib().seqalk_pair_score(ctypes.cast(xbuf, ctypes.c_void_p), len(xb), ctypes.cast(ybuf, ctypes.c_void_p),
+                                   len(yb), int(pxy), int(pgap), ctypes.byref(pen)))
+    return int(pen.value)
 
 
 def getMinimumPenalties(genes: Sequence, k: int, pxy: int, pgap: int, penalties) -> str:
@@ -348,6 +374,15 @@ class Job:
 
     def finish_async(self) -> None:
         _check(lib().seqalk_job_finish_async(self._h))
+
+    def run_scores(self, penalties_dev: int = 0) -> None:
+        """Score-only pass (penalties from the fill, no traceback / digest)."""
+        _check(lib().seqalk_job_run_scores(self._h, ctypes.c_void_p(penalties_dev or None)))
+
+    def fetch_penalties(self) -> np.ndarray:
+        pen = np.zeros(max(self.ntasks, 1), dtype=np.int32)
+        _check(lib().seqalk_job_fetch(self._h, pen.ctypes.data_as(_I32P), None))
+        return pen[: self.ntasks]
 
     def fetch(self) -> Tuple[np.ndarray, np.ndarray]:
         pen = np.zeros(max(self.ntasks, 1), dtype=np.int32)

@@ -196,7 +196,9 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
                     char digest_hex[129]) {
   const int N = (int)r.workers.size();
   const int64_t T = (int64_t)k * (k - 1) / 2;
-  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(8, T / 32768));
+  int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(8, T / 32768));
+  if (const char *e = std::getenv("SEQALK_PEER_CHUNKS"))  // tests: force several chunks on small jobs
+    nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(64, T), std::atoi(e)));
   // SEQALK_TRACE=1: phase times of this call on stderr
   const bool trace = std::getenv("SEQALK_TRACE") && std::atoi(std::getenv("SEQALK_TRACE"));
   const auto t0 = std::chrono::steady_clock::now();
@@ -423,6 +425,7 @@ void seqalk_shutdown(void) {
   r.release_results();
   r.workers.clear();
   pool().clear();
+  pinned_clear();
 }
 
 int seqalk_device_count(void) {
@@ -432,13 +435,18 @@ int seqalk_device_count(void) {
 }
 
 const char *seqalk_last_error(void) { return g_last_error.c_str(); }
-const char *seqalk_version(void) { return "seqalk-b200 0.1 (sm_100a)"; }
+const char *seqalk_version(void) { return "seqalk-b200 0.2 (sm_100a)"; }
 
 int seqalk_all_pairs(const char *const *seqs, const int32_t *lens, int32_t k, int32_t pxy, int32_t pgap,
                      int32_t *penalties_out, char digest_hex_out[129]) {
   try {
-    if (!seqs || !lens || !penalties_out || !digest_hex_out) return fail("null argument");
-    if (k < 2) return fail("k < 2 is undefined in the reference");
+    if (!digest_hex_out) return fail("null argument");
+    if (k < 0) return fail("negative sequence count");
+    if (k < 2) {  // no pairs: the reference returns the empty chain state and writes no penalty (:237, :282-287)
+      digest_hex_out[0] = 0;
+      return 0;
+    }
+    if (!seqs || !lens || !penalties_out) return fail("null argument");
     Runtime &r = rt();
     std::lock_guard<std::mutex> g(r.mu);
     ensure_init(r);
@@ -472,7 +480,8 @@ int seqalk_all_pairs(const char *const *seqs, const int32_t *lens, int32_t k, in
 int seqalk_pair(const char *x, int32_t m, const char *y, int32_t n, int32_t pxy, int32_t pgap, int32_t *xans,
                 int32_t *yans, int32_t *penalty_out) {
   try {
-    if (!x || !y) return fail("null argument");
+    if (m < 0 || n < 0) return fail("negative sequence length");
+    if ((m && !x) || (n && !y)) return fail("null argument");
     Runtime &r = rt();
     std::lock_guard<std::mutex> g(r.mu);
     ensure_init(r);
@@ -499,6 +508,86 @@ int seqalk_pair(const char *x, int32_t m, const char *y, int32_t n, int32_t pxy,
         if (yans) yans[a] = pad ? (int32_t)'_' : (int32_t)(char)a2[a - 1 - (l - L)];
       }
     }
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_all_pairs_scores(const char *const *seqs, const int32_t *lens, int32_t k, int32_t pxy, int32_t pgap,
+                            int32_t *penalties_out) {
+  try {
+    if (k < 0) return fail("negative sequence count");
+    if (k < 2) return 0;
+    if (!seqs || !lens || !penalties_out) return fail("null argument");
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> g(r.mu);
+    ensure_init(r);
+    SeqPack pack;
+    pack.build(seqs, lens, k);
+    const int N = (int)r.workers.size();
+    const int64_t T = (int64_t)k * (k - 1) / 2;
+    if (N == 1) {
+      std::vector<TaskIJ> tasks;
+      all_tasks(k, tasks);
+      DeviceWorker &w = *r.workers[0];
+      w.load(pack);
+      w.plan(tasks, pxy, pgap);
+      w.run_scores();
+      w.fetch(penalties_out, nullptr);
+      return 0;
+    }
+    // cell-balanced shards, one host thread per GPU, results scattered on the host (4 B per task)
+    std::vector<std::vector<int64_t>> per;
+    partition_lpt(pack.len.data(), k, 0, T, N, per);
+    std::vector<std::string> errors((size_t)N);
+    std::vector<std::vector<int32_t>> lpen((size_t)N);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < N; ++d)
+      threads.emplace_back([&, d]() {
+        try {
+          std::vector<TaskIJ> tasks(per[d].size());
+          for (size_t t = 0; t < tasks.size(); ++t) task_from_id(per[d][t], &tasks[t].i, &tasks[t].j);
+          DeviceWorker &w = *r.workers[d];
+          w.load(pack);
+          w.plan(tasks, pxy, pgap);
+          w.run_scores();
+          lpen[d].resize(tasks.size());
+          w.fetch(lpen[d].data(), nullptr);
+        } catch (const std::exception &e) {
+          errors[d] = e.what();
+          if (errors[d].empty()) errors[d] = "unknown error";
+        }
+      });
+    for (std::thread &t : threads) t.join();
+    for (int d = 0; d < N; ++d)
+      if (!errors[d].empty()) throw std::runtime_error("GPU " + std::to_string(d) + ": " + errors[d]);
+    for (int d = 0; d < N; ++d)
+      for (size_t t = 0; t < per[d].size(); ++t) penalties_out[per[d][t]] = lpen[d][t];
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int seqalk_pair_score(const char *x, int32_t m, const char *y, int32_t n, int32_t pxy, int32_t pgap,
+                      int32_t *penalty_out) {
+  try {
+    if (m < 0 || n < 0) return fail("negative sequence length");
+    if ((m && !x) || (n && !y) || !penalty_out) return fail("null argument");
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> g(r.mu);
+    ensure_init(r);
+    const char *seqs[2] = {y, x};
+    const int32_t lens[2] = {n, m};
+    SeqPack pack;
+    pack.build(seqs, lens, 2);
+    std::vector<TaskIJ> tasks(1, TaskIJ{1, 0});
+    DeviceWorker &w = *r.workers[0];
+    w.load(pack);
+    w.plan(tasks, pxy, pgap);
+    w.run_scores();
+    w.fetch(penalty_out, nullptr);
     return 0;
   } catch (const std::exception &e) {
     return fail(e);
@@ -679,6 +768,16 @@ int seqalk_job_run(seqalk_job_t *job, void *penalties_dev, void *digests_dev) {
   }
 }
 
+int seqalk_job_run_scores(seqalk_job_t *job, void *penalties_dev) {
+  try {
+    if (!job) return fail("null job");
+    job->worker->run_scores(static_cast<int32_t *>(penalties_dev));
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
 int seqalk_job_fetch(seqalk_job_t *job, int32_t *penalties_out, uint8_t *digests_out) {
   try {
     if (!job) return fail("null job");
@@ -704,6 +803,7 @@ int seqalk_job_stats(const seqalk_job_t *job, seqalk_stats_t *s) {
   s->wall_ms = j.wall_ms;
   s->tile_mode = j.tile_mode;
   s->fill_rows_per_lane = j.fill_rows_per_lane;
+  s->self_checked = j.self_checked;
   return 0;
 }
 

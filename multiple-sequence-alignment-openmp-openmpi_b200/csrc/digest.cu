@@ -168,7 +168,38 @@ __global__ void __launch_bounds__(DIGEST_THREADS, 16) digest_kernel(const Digest
   uint64_t *dst = reinterpret_cast<uint64_t *>(a.digests + (uint64_t)a.result_slot[p] * 64);
 #pragma unroll
   for (int k = 0; k < 8; ++k) dst[k] = bswap64(fin.s[k]);
-  a.penalties_out[a.result_slot[p]] = a.penalties[p];
+  const int32_t pen = a.penalties[p];
+  a.penalties_out[a.result_slot[p]] = pen;
+  if (a.corner_mode != CORNER_NONE) {
+    const PairDesc P = a.pairs[p];
+    if (P.m > 0 && P.n > 0) {
+      const int32_t score = a.brow[P.brow_off + corner_index(P, a.corner_mode)] + (P.m + P.n) * a.pgap;
+      if (score != pen) {
+        atomicAdd(a.check, 1u);
+        atomicMin(a.check + 1, (uint32_t)P.task_id);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) score_kernel(const ScoreArgs a) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.npairs) return;
+  const PairDesc P = a.pairs[p];
+  int32_t pen;
+  if (P.m == 0 || P.n == 0)
+    pen = (P.m + P.n) * a.pgap;
+  else if (a.corner_mode != CORNER_NONE)
+    pen = a.brow[P.brow_off + corner_index(P, a.corner_mode)] + (P.m + P.n) * a.pgap;
+  else
+    pen = a.path_cost[p];
+  a.penalties_out[a.result_slot[p]] = pen;
+}
+
+cudaError_t launch_scores(const ScoreArgs &args, cudaStream_t stream) {
+  if (args.npairs == 0) return cudaSuccess;
+  score_kernel<<<(args.npairs + 127) / 128, 128, 0, stream>>>(args);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_digest(const DigestArgs &args, cudaStream_t stream) {

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <queue>
 #include <stdexcept>
 
@@ -26,6 +27,71 @@ constexpr size_t EV = 6;  // timing events per batch
 // bounds the descriptor staging of a batch of very many tiny pairs (56 B + strips per pair)
 constexpr size_t MAX_PAIRS_PER_BATCH = 1u << 18;
 
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<uint8_t *, size_t>> idle;
+};
+PinnedPool &pinned_pool() {
+  static PinnedPool p;
+  return p;
+}
+}  // namespace
+
+uint8_t *pinned_acquire(size_t bytes, size_t *cap_out) {
+  PinnedPool &pp = pinned_pool();
+  {
+    std::lock_guard<std::mutex> g(pp.mu);
+    size_t best = pp.idle.size();
+    for (size_t i = 0; i < pp.idle.size(); ++i)
+      if (pp.idle[i].second >= bytes && (best == pp.idle.size() || pp.idle[i].second < pp.idle[best].second)) best = i;
+    if (best != pp.idle.size()) {
+      uint8_t *p = pp.idle[best].first;
+      *cap_out = pp.idle[best].second;
+      pp.idle.erase(pp.idle.begin() + (long)best);
+      return p;
+    }
+  }
+  void *p = nullptr;
+  const size_t want = round_up(bytes + bytes / 8 + 4096, 4096);
+  cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw std::runtime_error(std::string("cannot allocate page-locked staging memory (") + cudaGetErrorString(e) +
+                             "): libseqalk needs a CUDA device, there is no CPU fallback");
+  }
+  *cap_out = want;
+  return static_cast<uint8_t *>(p);
+}
+
+void pinned_release(uint8_t *p, size_t cap) {
+  if (!p) return;
+  PinnedPool &pp = pinned_pool();
+  std::lock_guard<std::mutex> g(pp.mu);
+  if (pp.idle.size() >= 4) {  // keep a handful; drop the smallest
+    size_t small = 0;
+    for (size_t i = 1; i < pp.idle.size(); ++i)
+      if (pp.idle[i].second < pp.idle[small].second) small = i;
+    if (pp.idle[small].second < cap) {
+      cudaFreeHost(pp.idle[small].first);
+      pp.idle[small] = {p, cap};
+    } else {
+      cudaFreeHost(p);
+    }
+    return;
+  }
+  pp.idle.emplace_back(p, cap);
+}
+
+void pinned_clear() {
+  PinnedPool &pp = pinned_pool();
+  std::lock_guard<std::mutex> g(pp.mu);
+  for (auto &b : pp.idle) cudaFreeHost(b.first);
+  pp.idle.clear();
+}
+
+SeqPack::~SeqPack() { pinned_release(bytes, cap); }
+
 void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
   k = k_;
   off.resize(k);
@@ -33,12 +99,17 @@ void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
   size_t total = 0;
   for (int i = 0; i < k; ++i) {
     if (lens[i] < 0) throw std::runtime_error("negative sequence length");
+    if (lens[i] > 0 && !seqs[i]) throw std::runtime_error("null sequence pointer");
     off[i] = (uint32_t)total;
     total += round_up((size_t)lens[i], 16) + 16;
     if (total > 0xfff00000ull) throw std::runtime_error("input larger than 4 GiB is not supported");
   }
-  bytes.assign(total + BUFFER_SLACK, 0);
-  for (int i = 0; i < k; ++i) std::memcpy(bytes.data() + off[i], seqs[i], (size_t)lens[i]);
+  size = total + BUFFER_SLACK;
+  if (bytes) pinned_release(bytes, cap);
+  bytes = pinned_acquire(size, &cap);
+  std::memset(bytes, 0, size);
+  for (int i = 0; i < k; ++i)
+    if (lens[i]) std::memcpy(bytes + off[i], seqs[i], (size_t)lens[i]);
   // alphabet: with <= 4 distinct letters (DNA) the fill can use a per-row cost table; the
   // letters are remapped on the GPU (remap_letters) from this 256-entry table
   uint8_t seen[256] = {0};
@@ -53,6 +124,7 @@ void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
       if (nletters < 4) code_of[ch] = (uint8_t)(8 * nletters);  // stored as the byte's bit offset
       ++nletters;
     }
+  has_underscore = seen[(unsigned char)'_'] != 0;
 }
 
 namespace {
@@ -181,6 +253,7 @@ DeviceWorker::~DeviceWorker() {
   release(codes_);
   release(res_pen_);
   release(res_dig_);
+  release(check_);
   if (h_res_) cudaFreeHost(h_res_);
   for (cudaEvent_t e : ev_) cudaEventDestroy(e);
 }
@@ -226,12 +299,14 @@ void DeviceWorker::load(const SeqPack &pack) {
   pack_copy_.off = pack.off;
   pack_copy_.len = pack.len;
   pack_copy_.nletters = pack.nletters;
+  pack_copy_.has_underscore = pack.has_underscore;
   pack_ = &pack_copy_;
-  ensure(seq_, (pack.bytes.size() + 15) / 16 * 16);  // the letter remap reads whole 16 B words
-  SEQALK_CUDA(cudaMemcpyAsync(seq_.p, pack.bytes.data(), pack.bytes.size(), cudaMemcpyHostToDevice,
-                              fill_stream_));
+  strip_scan_ = pack.has_underscore;
+  ensure(seq_, (pack.size + 15) / 16 * 16);  // the letter remap reads whole 16 B words
+  // source is page-locked (SeqPack): a true asynchronous DMA
+  SEQALK_CUDA(cudaMemcpyAsync(seq_.p, pack.bytes, pack.size, cudaMemcpyHostToDevice, fill_stream_));
   if (pack.nletters <= 4) {
-    const size_t n16 = (pack.bytes.size() + 15) / 16;
+    const size_t n16 = (pack.size + 15) / 16;
     ensure(codes_, n16 * 16);
     Lut256 lut;
     std::memcpy(lut.v, pack.code_of, 256);
@@ -245,6 +320,8 @@ void DeviceWorker::load(const SeqPack &pack) {
 void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
                         const std::vector<uint32_t> *result_slots, const std::vector<size_t> *chunk_ends) {
   if (!pack_) throw std::runtime_error("plan() before load()");
+  finish_async();  // never re-plan under a running asynchronous pass
+  ran_ = false;
   tasks_ = tasks;
   if (result_slots) {
     if (result_slots->size() != tasks.size()) throw std::runtime_error("result_slots size mismatch");
@@ -327,10 +404,12 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     const TaskIJ &tk = tasks_[t];
     if (tk.i < 0 || tk.i >= pack_->k || tk.j < 0 || tk.j >= pack_->k) throw std::runtime_error("task index out of range");
     const int m = pack_->len[tk.i], n = pack_->len[tk.j];
-    if (m < 1 || n < 1)
-      throw std::runtime_error("empty sequence: undefined in the reference (ceil(0/0) tile size, submit/xuliny-seqalkway.cpp:457)");
     maxlen = std::max<int64_t>(maxlen, std::max(m, n));
-    const StripGeom geo = strip_geometry(m, R, mixed_);
+    // an empty sequence (undefined in the parallel reference: ceil(0/0) tile size at
+    // submit/xuliny-seqalkway.cpp:457; the sequential twin :570-663 returns (m+n)*pgap with a
+    // pure-tail alignment) has no DP cells: no strips, the traceback only writes the tails
+    StripGeom geo = strip_geometry(m, R, mixed_);
+    if (m < 1 || n < 1) geo.nstrips = 0, geo.half_last = 0;
     const uint32_t ns = (uint32_t)geo.nstrips;
     const uint64_t brow_ints = tiles_ ? (uint64_t)(geo.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(n) + 4)
                                       : 4ull * (uint64_t)macro_cols(n) + 4;
@@ -400,25 +479,58 @@ void DeviceWorker::run_chunk(size_t c, int32_t *penalties_dev, uint8_t *digests_
   run_impl(penalties_dev, digests_dev, nullptr, nullptr, chunk_batch_[c], chunk_batch_[c + 1]);
 }
 
+void DeviceWorker::run_scores(int32_t *penalties_dev) {
+  run_impl(penalties_dev, nullptr, nullptr, nullptr, 0, batches_.size(), true);
+}
+
+void DeviceWorker::verify_check() {
+  if (!check_.p) return;
+  uint32_t c[2] = {0, 0};
+  SEQALK_CUDA(cudaMemcpy(c, check_.p, sizeof c, cudaMemcpyDeviceToHost));
+  if (c[0]) {
+    char msg[256];
+    std::snprintf(msg, sizeof msg,
+                  "internal check failed: for %u task(s) the traceback's path cost differs from the fill's "
+                  "dp[m][n] (first: task %u of this job)", c[0], c[1]);
+    throw std::runtime_error(msg);
+  }
+}
+
 void DeviceWorker::run_and_fold(int32_t *penalties_host, char digest_hex_out[129]) {
   if (!result_slots_.empty()) throw std::runtime_error("run_and_fold needs identity result slots");
   run_impl(nullptr, nullptr, penalties_host, digest_hex_out, 0, batches_.size());
 }
 
 void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties,
-                            char *fold_hex, size_t batch_begin, size_t batch_end) {
+                            char *fold_hex, size_t batch_begin, size_t batch_end, bool scores_only) {
   SEQALK_CUDA(cudaSetDevice(dev_));
   const bool streaming = fold_hex != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
   const int R = variant_.R;
   const size_t T = tasks_.size();
+  results_in_caller_pen_ = penalties_dev != nullptr;
+  results_in_caller_dig_ = digests_dev != nullptr;
+  have_digests_ = !scores_only;
   if (!penalties_dev) {
     ensure(res_pen_, std::max<size_t>(T, 1) * sizeof(int32_t));
     penalties_dev = static_cast<int32_t *>(res_pen_.p);
   }
-  if (!digests_dev) {
+  if (!digests_dev && !scores_only) {
     ensure(res_dig_, std::max<size_t>(T, 1) * 64);
     digests_dev = static_cast<uint8_t *>(res_dig_.p);
+  }
+  // The fill's own dp[m][n] is available in table mode (row_operand, fill_core.cuh): the digest
+  // kernel compares it with the traceback's path cost for every pair (SEQALK_SELFCHECK=0: off).
+  int corner_mode = variant_.mode == MODE_TAB ? (tiles_ ? CORNER_TILES : CORNER_DIRS) : CORNER_NONE;
+  const bool fill_only = scores_only && corner_mode != CORNER_NONE;
+  if (!scores_only)
+    if (const char *e = std::getenv("SEQALK_SELFCHECK"))
+      if (!std::atoi(e)) corner_mode = CORNER_NONE;
+  ensure(check_, 2 * sizeof(uint32_t));
+  if (batch_begin == 0) {
+    const uint32_t init[2] = {0u, 0xffffffffu};
+    SEQALK_CUDA(cudaMemcpyAsync(check_.p, init, sizeof init, cudaMemcpyHostToDevice, fill_stream_));
+    stats_.self_checked = (!scores_only && corner_mode != CORNER_NONE) ? 1 : 0;
   }
   int32_t *h_pen = nullptr;
   uint8_t *h_dig = nullptr;
@@ -519,7 +631,8 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       d.brow_off = brow_off;
       d.out_off = out_off;
       d.strip0 = strip0;
-      const StripGeom geo = strip_geometry(d.m, R, mixed_);
+      StripGeom geo = strip_geometry(d.m, R, mixed_);
+      if (d.m < 1 || d.n < 1) geo.nstrips = 0, geo.half_last = 0;
       d.nstrips = geo.nstrips;
       d.mpad = geo.mpad;
       d.half_last = geo.half_last;
@@ -616,20 +729,38 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.mode = variant_.mode;
     ta.addmode = variant_.addmode;
     ta.long_pairs = few_pairs_ ? 1 : 0;
+    ta.strip_scan = strip_scan_ ? 1 : 0;
     if (const char *e = std::getenv("SEQALK_TB_LONG")) ta.long_pairs = std::atoi(e) ? 1 : 0;
-    SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
+    if (!fill_only) SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));
 
-    DigestArgs da;
-    da.pairs = fa.pairs;
-    da.npairs = (uint32_t)B.count;
-    da.out = ta.out;
-    da.align = ta.align;
-    da.penalties = ta.path_cost;
-    da.result_slot = static_cast<const uint32_t *>(S.slots.p);
-    da.digests = digests_dev;
-    da.penalties_out = penalties_dev;
-    SEQALK_CUDA(launch_digest(da, st));
+    if (scores_only) {
+      ScoreArgs sa;
+      sa.pairs = fa.pairs;
+      sa.npairs = (uint32_t)B.count;
+      sa.brow = fa.brow;
+      sa.corner_mode = corner_mode;
+      sa.pgap = pgap_;
+      sa.path_cost = ta.path_cost;
+      sa.result_slot = static_cast<const uint32_t *>(S.slots.p);
+      sa.penalties_out = penalties_dev;
+      SEQALK_CUDA(launch_scores(sa, st));
+    } else {
+      DigestArgs da;
+      da.pairs = fa.pairs;
+      da.npairs = (uint32_t)B.count;
+      da.out = ta.out;
+      da.align = ta.align;
+      da.penalties = ta.path_cost;
+      da.result_slot = static_cast<const uint32_t *>(S.slots.p);
+      da.digests = digests_dev;
+      da.penalties_out = penalties_dev;
+      da.brow = fa.brow;
+      da.corner_mode = corner_mode;
+      da.pgap = pgap_;
+      da.check = static_cast<uint32_t *>(check_.p);
+      SEQALK_CUDA(launch_digest(da, st));
+    }
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 4], st));
     if (streaming) {
       SEQALK_CUDA(cudaMemcpyAsync(h_pen + B.first, penalties_dev + B.first, B.count * sizeof(int32_t),
@@ -652,13 +783,15 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       }
     if (streaming) fold_ready(false, b + 1);  // fold what has landed while the GPU works on later batches
     stats_.fill_launches++;
-    stats_.traceback_launches++;
+    if (!fill_only) stats_.traceback_launches++;
     stats_.digest_launches++;
   }
   if (streaming) fold_ready(true, batch_end);
   SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
   SEQALK_CUDA(cudaStreamSynchronize(post_stream_));
   for (Slot &S : slots_) S.staged_pending = S.post_pending = false;
+  if (batch_end == batches_.size() && !scores_only) verify_check();
+  ran_ = true;
   for (size_t b = batch_begin; b < batch_end; ++b) {
     float ms = 0;
     SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[EV * b + 0], ev_[EV * b + 1]));
@@ -726,9 +859,16 @@ void DeviceWorker::fetch(int32_t *penalties_host, uint8_t *digests_host) {
   SEQALK_CUDA(cudaSetDevice(dev_));
   const size_t T = tasks_.size();
   if (!T) return;
-  if (penalties_host)
+  if (penalties_host) {
+    if (results_in_caller_pen_ || !res_pen_.p || !ran_)
+      throw std::runtime_error("fetch: the last run wrote its penalties to caller-supplied device memory (or did not run)");
     SEQALK_CUDA(cudaMemcpy(penalties_host, res_pen_.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (digests_host) SEQALK_CUDA(cudaMemcpy(digests_host, res_dig_.p, T * 64, cudaMemcpyDeviceToHost));
+  }
+  if (digests_host) {
+    if (results_in_caller_dig_ || !have_digests_ || !res_dig_.p || !ran_)
+      throw std::runtime_error("fetch: the last run wrote its digests to caller-supplied device memory (or produced none)");
+    SEQALK_CUDA(cudaMemcpy(digests_host, res_dig_.p, T * 64, cudaMemcpyDeviceToHost));
+  }
 }
 
 bool DeviceWorker::fetch_alignment(size_t index_in_job, std::vector<uint8_t> &a1, std::vector<uint8_t> &a2) {

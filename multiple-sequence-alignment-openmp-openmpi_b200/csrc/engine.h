@@ -21,15 +21,29 @@ namespace seqalk {
 
 // Host copy of the input in the layout the kernels read: every sequence starts on a
 // 16 B boundary and is followed by >= 16 zero bytes (the fill reads y in 4-byte words).
+// The bytes live in page-locked host memory taken from a process-wide pool (pinned_acquire /
+// pinned_release), so the H2D copy of the sequences is a real asynchronous DMA and repeated calls
+// do not pay cudaHostAlloc again (the reference's input path: std::cin >> genes[i],
+// submit/xuliny-seqalkway.cpp:44-48, then MPI_Bcast :249-266).
 struct SeqPack {
-  std::vector<uint8_t> bytes;
+  uint8_t *bytes = nullptr;    // pinned, `size` bytes used of `cap`
+  size_t size = 0, cap = 0;
   std::vector<uint32_t> off;
   std::vector<int32_t> len;
   int nletters = 256;          // distinct byte values in the input
   uint8_t code_of[256];        // <= 4 letters: letter -> 8*(0..3) (bit offset of its cost-table byte)
+  bool has_underscore = false; // '_' (the gap character) occurs inside a sequence
   int k = 0;
+  SeqPack() = default;
+  SeqPack(const SeqPack &) = delete;
+  SeqPack &operator=(const SeqPack &) = delete;
+  ~SeqPack();
   void build(const char *const *seqs, const int32_t *lens, int k);
 };
+// Page-locked staging buffers, cached between calls; pinned_clear() frees them (seqalk_shutdown).
+uint8_t *pinned_acquire(size_t bytes, size_t *cap_out);
+void pinned_release(uint8_t *p, size_t cap);
+void pinned_clear();
 
 struct TaskIJ {
   int32_t i, j;  // x = seq[i] (rows), y = seq[j] (columns)
@@ -45,6 +59,7 @@ struct JobStats {
   double wall_ms = 0;          // host wall time of run()
   uint32_t tile_mode = 0;      // 1: score-only fill + tile-recompute traceback; 0: directions in HBM
   uint32_t fill_rows_per_lane = 0;
+  uint32_t self_checked = 0;   // 1: every penalty was compared on the device with the fill's own dp[m][n]
 };
 
 class DeviceWorker {
@@ -69,6 +84,10 @@ class DeviceWorker {
   // both may be null (-> worker-owned device arrays, read back with fetch()) or point
   // into another GPU's memory when peer access is enabled (fused gather over NVLink).
   void run(int32_t *penalties_dev = nullptr, uint8_t *digests_dev = nullptr);
+  // Score-only pass (reference result dp[m][n], submit/xuliny-seqalkway.cpp:560): penalties
+  // without alignment strings or digests.  With <= 4 letters the fill alone produces them (no
+  // traceback); other alphabets run fill + traceback and return the path cost.
+  void run_scores(int32_t *penalties_dev = nullptr);
   // Runs only chunk c (see plan); the pointers address the WHOLE job's result arrays.
   void run_chunk(size_t c, int32_t *penalties_dev = nullptr, uint8_t *digests_dev = nullptr);
   size_t num_chunks() const { return chunk_batch_.empty() ? 0 : chunk_batch_.size() - 1; }
@@ -140,7 +159,13 @@ class DeviceWorker {
   Batch need_{0, 0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches
   DevBuf res_pen_, res_dig_;
   void run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_t *fold_penalties, char *fold_hex,
-                size_t batch_begin, size_t batch_end);
+                size_t batch_begin, size_t batch_end, bool scores_only = false);
+  // where the last run wrote its results (fetch() can only serve worker-owned arrays)
+  bool results_in_caller_pen_ = false, results_in_caller_dig_ = false, have_digests_ = false;
+  bool ran_ = false;           // a pass over the planned job has completed since plan()
+  bool strip_scan_ = false;    // the input contains '_'
+  DevBuf check_;               // self-check counters: [0] mismatches, [1] smallest failing task id
+  void verify_check();         // throws if the device-side fill/traceback cross-check failed
   std::vector<size_t> chunk_batch_;  // chunk c = batches [chunk_batch_[c], chunk_batch_[c+1])
   std::vector<cudaEvent_t> chunk_ev_;  // results of chunk c are in the result arrays
   std::thread async_thread_;

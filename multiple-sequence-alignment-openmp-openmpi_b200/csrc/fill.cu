@@ -178,7 +178,7 @@ __device__ __forceinline__ void process_strip(const FillArgs &a, const PairDesc 
         yw = ny;
         macro_step<R, MODE, ADDMODE, EMIT>(h, dg, xc, up_in, yw, A, B, one, minus_one, outv, bits);
         if (EMIT) {
-          if (lane == 31 && !last) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);
+          if (lane == 31) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);  // last strip: H'[m][.] (row_operand)
         } else {
           // every TILE_ROWS rows (R = 32: lanes 3, 7, ..., 31) keep the row for the tile traceback
           if ((lane & (TILE_ROWS / R - 1)) == (TILE_ROWS / R - 1)) brow_wr[qc] = make_int4(outv[0], outv[1], outv[2], outv[3]);

@@ -114,14 +114,19 @@ __device__ __forceinline__ void macro_step(int (&h)[R], int &dg, const int (&xc)
 
 
 // Row operand of macro_step for one DP row: the 4-letter cost table (MODE_TAB, `ch` is 8 x the
-// letter code, i.e. 0/8/16/24) or the raw character; rows past the end of x never match.
+// letter code, i.e. 0/8/16/24) or the raw character.
+// Rows past the end of x: MODE_TAB gives them an all-zero table (cost 0 against every letter).
+// H' never increases down a column or along a row, so with cost 0 such a row takes
+// min3(diag, up, left) = up: every padded row is a copy of DP row m, and the strip's bottom row —
+// which the fill stores anyway — carries H'[m][1..n].  The corner H'[m][n] read from there is the
+// fill's own score (score-only entry points, and the on-device check of the traceback's path
+// cost).  Other modes: a character that never matches (their padded rows hold no usable value).
 template <int MODE>
 __device__ __forceinline__ int row_operand(bool inside, int ch, int r, int A, int B) {
   if (MODE == MODE_TAB) {
+    if (!inside) return 0;
     const unsigned Ab = (unsigned)A & 0xffu, Bb = (unsigned)B & 0xffu;
-    unsigned tab = Bb * 0x01010101u;
-    if (inside) tab ^= (Ab ^ Bb) << (ch & 24);  // ch = 8 * letter code
-    return (int)tab;
+    return (int)((Bb * 0x01010101u) ^ ((Ab ^ Bb) << (ch & 24)));  // ch = 8 * letter code
   }
   return inside ? ch : (0x100 + r);
 }

@@ -65,7 +65,19 @@ struct TracebackArgs {
                             // satisfies dp[cell] = dp[predecessor] + step cost, and dp[i][0] = i*pgap)
   int32_t pxy, pgap;
   int32_t R;                // rows per lane the fill used (direction layout)
+  int32_t strip_scan;       // 1: the input contains '_' (the gap character): apply the reference's
+                            // strip rule literally (submit/xuliny-seqalkway.cpp:191-202): the alignment
+                            // starts after the LAST column holding '_' in both strings
 };
+
+// Where the fill left H'[m][n] of a pair (MODE_TAB only: padded rows copy DP row m, so the bottom
+// row of the pair's last strip is H'[m][1..n]; see row_operand in fill_core.cuh).
+enum : int { CORNER_NONE = 0, CORNER_TILES = 1, CORNER_DIRS = 2 };
+__host__ __device__ inline uint64_t corner_index(const PairDesc &P, int corner_mode) {
+  const uint64_t nq = (uint64_t)((P.n + 3) >> 2);
+  return corner_mode == CORNER_TILES ? (uint64_t)(P.mpad / TILE_ROWS - 1) * (4 * nq + 4) + (uint64_t)(P.n - 1)
+                                     : (uint64_t)(P.n - 1);
+}
 
 struct DigestArgs {
   const PairDesc *pairs;
@@ -76,6 +88,26 @@ struct DigestArgs {
   const uint32_t *result_slot;  // per pair of the batch: slot in the job-wide result arrays
   uint8_t *digests;             // job-wide: 64 raw bytes per slot (may be a peer GPU's memory)
   int32_t *penalties_out;       // job-wide: penalty per slot (may be a peer GPU's memory)
+  // self-check: the fill's own dp[m][n] (corner_mode != CORNER_NONE) must equal the traceback's
+  // path cost; mismatches are counted in check[0], the smallest failing task id goes to check[1]
+  const int32_t *brow;
+  int32_t corner_mode;
+  int32_t pgap;
+  uint32_t *check;
+};
+
+// Score-only result: penalties without alignment strings (reference result dp[m][n],
+// submit/xuliny-seqalkway.cpp:560).  corner_mode != CORNER_NONE: read from the fill's bottom row;
+// else copy the traceback's path cost.
+struct ScoreArgs {
+  const PairDesc *pairs;
+  uint32_t npairs;
+  const int32_t *brow;
+  int32_t corner_mode;
+  int32_t pgap;
+  const int32_t *path_cost;
+  const uint32_t *result_slot;
+  int32_t *penalties_out;
 };
 
 cudaError_t launch_fill(const FillArgs &args, const FillVariant &v, int sm_count, cudaStream_t stream);
@@ -83,5 +115,6 @@ int fill_blocks_per_sm(const FillVariant &v);
 cudaError_t launch_traceback(const TracebackArgs &args, cudaStream_t stream);
 cudaError_t launch_traceback_tiles(const TracebackArgs &args, cudaStream_t stream);
 cudaError_t launch_digest(const DigestArgs &args, cudaStream_t stream);
+cudaError_t launch_scores(const ScoreArgs &args, cudaStream_t stream);
 
 }  // namespace seqalk

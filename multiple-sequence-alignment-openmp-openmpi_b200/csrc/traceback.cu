@@ -102,9 +102,17 @@ __global__ void __launch_bounds__(TRACEBACK_THREADS) traceback_kernel(const Trac
     w1.put('_');
     w2.put(ys[j - 1]);
   }
-  const uint32_t start = w1.pos;
+  uint32_t start = w1.pos;
   w1.finish();
   w2.finish();
+  if (a.strip_scan) {  // '_' inside the inputs: the reference's scan for the last common '_' column
+    const uint8_t *o1 = a.out + P.out_off, *o2 = o1 + P.cap;
+    for (uint32_t c = (uint32_t)(m + n); c > start; --c)
+      if (o1[c - 1] == '_' && o2[c - 1] == '_') {
+        start = c;
+        break;
+      }
+  }
   PairAlign r;
   r.start = start;
   r.len = (uint32_t)(m + n) - start;

@@ -253,6 +253,20 @@ __device__ __forceinline__ void finish_pair(const TracebackArgs &a, const TileCt
     W.o2[W.pos - 1 - t] = T.ys[j - 1 - t];
   }
   W.pos -= j;
+  if (a.strip_scan) {
+    // '_' inside the inputs: the reference strips everything up to the LAST column that holds
+    // '_' in both strings (submit/xuliny-seqalkway.cpp:191-202), not only the leading pad
+    __syncwarp();
+    const int L = T.m + T.n;
+    int found = -1;
+    for (int base = L - 32; base + 31 >= W.pos && found < 0; base -= 32) {
+      const int idx = base + lane;
+      const bool hit = idx >= W.pos && idx < L && W.o1[idx] == '_' && W.o2[idx] == '_';
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      if (b) found = base + 31 - __clz(b);
+    }
+    if (found >= 0) W.pos = found + 1;
+  }
   int cost = W.cost;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, d);

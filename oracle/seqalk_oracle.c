@@ -123,13 +123,18 @@ enum { DIR_DIAG = 0, DIR_UP = 1, DIR_LEFT = 2 };
  * gapped strings with the common leading pad removed (capacity m+n+1 each,
  * NUL-terminated), *alen their length; hash_hex = problemhash
  * = H(H(align1) ++ H(align2)).
- * Returns 0, or -1 on allocation failure / m<1 / n<1 (undefined upstream).
+ * The alignment starts after the LAST column holding '_' in both strings
+ * (skeleton:135-145): for inputs without a literal '_' that is the leading
+ * pad; with '_' inside the inputs the reference cuts later, and so does this.
+ * m = 0 or n = 0 follow the sequential skeleton (:186-280: penalty (m+n)*pgap,
+ * pure tails; the submission's tiled twin divides by zero there).
+ * Returns 0, or -1 on allocation failure / negative length.
  */
 int oracle_pair(const char *x, int m, const char *y, int n, int pxy, int pgap, int *penalty,
                 char *align1, char *align2, int *alen, char hash_hex[129]) {
-  if (m < 1 || n < 1) return -1;
+  if (m < 0 || n < 0) return -1;
   size_t stride = ((size_t)n + 3) / 4; /* bytes per direction row (cells j=1..n) */
-  unsigned char *dirs = (unsigned char *)calloc((size_t)m * stride, 1);
+  unsigned char *dirs = (unsigned char *)calloc((size_t)m * stride + 1, 1);
   int *prev = (int *)malloc(sizeof(int) * ((size_t)n + 1));
   int *cur = (int *)malloc(sizeof(int) * ((size_t)n + 1));
   if (!dirs || !prev || !cur) {
@@ -185,6 +190,15 @@ int oracle_pair(const char *x, int m, const char *y, int n, int pxy, int pgap, i
     for (size_t a = 0; a < len; ++a) { a1[o + a] = r1[len - 1 - a]; a2[o + a] = r2[len - 1 - a]; }
     o += len;
     a1[o] = 0; a2[o] = 0;
+    /* strip scan (skeleton:135-145): columns up to the last '_'/'_' column are dropped */
+    size_t first = 0;
+    for (size_t a = o; a > 0; --a)
+      if (a1[a - 1] == '_' && a2[a - 1] == '_') { first = a; break; }
+    if (first) {
+      memmove(a1, a1 + first, o - first + 1);
+      memmove(a2, a2 + first, o - first + 1);
+      o -= first;
+    }
     if (alen) *alen = (int)o;
     if (hash_hex) {
       char cat[257];

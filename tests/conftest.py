@@ -53,3 +53,15 @@ def load_fixture(workloads, golden):
         return pxy, pgap, genes, e
 
     return _load
+
+
+@pytest.fixture(scope="session")
+def underscore_cases():
+    """Inputs containing '_' with the unmodified reference's outputs (tests/golden/make_golden.py)."""
+    return json.load(open(os.path.join(GOLDEN_DIR, "underscore.json")))
+
+
+@pytest.fixture(scope="session")
+def fullsize():
+    """Oracle goldens of BASELINE configs 3-5 at full size (tests/golden/make_golden_fullsize.py)."""
+    return json.load(open(os.path.join(GOLDEN_DIR, "fullsize.json")))

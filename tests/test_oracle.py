@@ -72,6 +72,37 @@ def test_oracle_matches_unmodified_reference_fuzz(oracle, workloads):
         assert list(op) == rp
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "ref_seq")),
+                    reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_underscore_inputs_match_unmodified_reference(oracle, workloads):
+    """'_' inside the inputs: the reference's strip scan (skeleton:135-145) cuts the alignment at the
+    LAST column with '_' in both strings, not only at the leading pad."""
+    rnd = random.Random(95)
+    for it in range(30):
+        k = rnd.randint(2, 5)
+        alpha = rnd.choice([b"A_", b"AC_", b"ACG_", b"ACGT_", b"__A"])
+        genes = [bytes(rnd.choice(alpha) for _ in range(rnd.randint(1, 120))) for _ in range(k)]
+        pxy, pgap = rnd.choice([0, 1, 3, 5]), rnd.choice([0, 1, 2, 4])
+        doc = workloads.format_input(pxy, pgap, genes)
+        _, rd, rp = oracle.run_reference(oracle.REF_SEQ if it % 3 else oracle.REF_PAR, doc, timeout=120)
+        od, op, _ = oracle.all_pairs(genes, pxy, pgap)
+        assert od == rd, (it, pxy, pgap, genes)
+        assert list(op) == rp
+
+
+def test_oracle_underscore_golden(oracle, underscore_cases):
+    for c in underscore_cases:
+        od, op, _ = oracle.all_pairs([g.encode("latin-1") for g in c["genes"]], c["pxy"], c["pgap"])
+        assert od == c["digest"] and list(op) == c["penalties"]
+
+
+def test_oracle_empty_sequence_follows_sequential_skeleton(oracle):
+    pen, a1, a2, _ = oracle.pair(b"", b"ACGT", 3, 2)
+    assert (pen, a1, a2) == (8, b"____", b"ACGT")
+    pen, a1, a2, _ = oracle.pair(b"AC", b"", 3, 2)
+    assert (pen, a1, a2) == (4, b"AC", b"__")
+
+
 def test_oracle_negative_penalties_match_reference_semantics(oracle):
     """Negative penalties are legal integers for the reference; the oracle follows the same
     'match takes the diagonal, traceback tests in order' rules (checked against _ref in the
