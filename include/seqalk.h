@@ -108,6 +108,7 @@ typedef struct seqalk_stats {
   double wall_ms;             /* host wall time of the last seqalk_job_run */
   uint32_t tile_mode;         /* 1: score-only fill + tile-recompute traceback, 0: directions in HBM */
   uint32_t fill_rows_per_lane;
+  uint32_t fill_packed16;     /* 1: the tile-mode fill ran as the 16x2-packed kernel (two DP cells per register) */
   uint32_t self_checked;      /* 1: every penalty was compared on the device with the fill's own dp[m][n] */
 } seqalk_stats_t;
 

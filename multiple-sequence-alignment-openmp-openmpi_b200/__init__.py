@@ -51,7 +51,7 @@ class _Stats(ctypes.Structure):
         ("digest_launches", ctypes.c_uint32), ("fill_ms", ctypes.c_double),
         ("traceback_ms", ctypes.c_double), ("digest_ms", ctypes.c_double), ("wall_ms", ctypes.c_double),
         ("tile_mode", ctypes.c_uint32), ("fill_rows_per_lane", ctypes.c_uint32),
-        ("self_checked", ctypes.c_uint32),
+        ("fill_packed16", ctypes.c_uint32), ("self_checked", ctypes.c_uint32),
     ]
 
 

@@ -804,6 +804,7 @@ int seqalk_job_stats(const seqalk_job_t *job, seqalk_stats_t *s) {
   s->tile_mode = j.tile_mode;
   s->fill_rows_per_lane = j.fill_rows_per_lane;
   s->self_checked = j.self_checked;
+  s->fill_packed16 = j.fill_packed16;
   return 0;
 }
 

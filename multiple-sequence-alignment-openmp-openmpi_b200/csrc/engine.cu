@@ -101,7 +101,7 @@ void SeqPack::build(const char *const *seqs, const int32_t *lens, int k_) {
     if (lens[i] < 0) throw std::runtime_error("negative sequence length");
     if (lens[i] > 0 && !seqs[i]) throw std::runtime_error("null sequence pointer");
     off[i] = (uint32_t)total;
-    total += round_up((size_t)lens[i], 16) + 16;
+    total += round_up((size_t)lens[i], 16) + SEQ_PAD;
     if (total > 0xfff00000ull) throw std::runtime_error("input larger than 4 GiB is not supported");
   }
   size = total + BUFFER_SLACK;
@@ -251,6 +251,8 @@ DeviceWorker::~DeviceWorker() {
   if (post_stream_) cudaStreamDestroy(post_stream_);
   release(seq_);
   release(codes_);
+  release(sel16_);
+  release(seqmeta_);
   release(res_pen_);
   release(res_dig_);
   release(check_);
@@ -313,6 +315,18 @@ void DeviceWorker::load(const SeqPack &pack) {
     remap_letters_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 4096), 256, 0, fill_stream_>>>(
         static_cast<const uint8_t *>(seq_.p), static_cast<uint8_t *>(codes_.p), n16, lut);
     SEQALK_CUDA(cudaGetLastError());
+    // selector streams of the 16x2-packed fill (fill16.cu): 8 bytes per macro column of every
+    // sequence, at twice the sequence's offset
+    ensure(sel16_, 2 * n16 * 16);
+    ensure(seqmeta_, (size_t)pack.k * 8 + 16);
+    uint32_t *off_dev = static_cast<uint32_t *>(seqmeta_.p);
+    int32_t *len_dev = reinterpret_cast<int32_t *>(off_dev + pack.k);
+    SEQALK_CUDA(cudaMemcpyAsync(off_dev, pack.off.data(), (size_t)pack.k * 4, cudaMemcpyHostToDevice, fill_stream_));
+    SEQALK_CUDA(cudaMemcpyAsync(len_dev, pack.len.data(), (size_t)pack.k * 4, cudaMemcpyHostToDevice, fill_stream_));
+    int maxlen = 0;
+    for (int32_t L : pack.len) maxlen = std::max(maxlen, L);
+    SEQALK_CUDA(launch_build_sel16(static_cast<const uint8_t *>(codes_.p), static_cast<uint8_t *>(sel16_.p), off_dev,
+                                   len_dev, pack.k, maxlen, fill_stream_));
   }
   SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
 }
@@ -384,8 +398,27 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     few_pairs_ = strips < 2ull * (uint64_t)sm_count_ * 16;
     if (few_pairs_ && tiles_ && !std::getenv("SEQALK_FILL_R")) variant_.R = 16;
   }
-  const int R = variant_.R;
   int64_t maxlen = 1;
+  for (const TaskIJ &tk : tasks_) maxlen = std::max<int64_t>(maxlen, std::max(pack_->len[tk.i], pack_->len[tk.j]));
+  // fast path needs non-negative penalties and scores far from int32 overflow
+  // (|H'| <= 2*max(pxy,pgap)*(m+n)); anything else takes the exact-select kernel.
+  const int64_t pmax = std::max<int64_t>(std::max(pxy, pgap), 1);
+  bool general = pxy < 0 || pgap < 0 || pmax * 4 * maxlen >= (1ll << 29);
+  if (const char *e = std::getenv("SEQALK_FORCE_GENERAL"))
+    if (std::atoi(e)) general = true;
+  // cost table (PRMT) needs <= 4 letters and both shifted costs in a signed byte
+  bool table = pack_->nletters <= 4 && 2 * (int64_t)pgap <= 127 && (int64_t)pxy - 2 * (int64_t)pgap <= 127 &&
+               (int64_t)pxy - 2 * (int64_t)pgap >= -128;
+  if (const char *e = std::getenv("SEQALK_FILL_TAB"))
+    if (!std::atoi(e)) table = false;
+  variant_.mode = general ? MODE_GENERAL : (table ? MODE_TAB : MODE_CMP);
+  // 16x2-packed fill (fill16.cu): tile mode, cost table, 1024 / 512-row strip pairs (the geometry
+  // of the 32-rows-per-lane fill), penalties small enough for 16-bit relative scores
+  fill16_shift_ = 0;
+  if (tiles_ && variant_.mode == MODE_TAB && variant_.R == 32 && mixed_ && codes_.p) fill16_shift_ = fill16_rebase_shift(pxy, pgap);
+  if (const char *e = std::getenv("SEQALK_FILL16"))
+    if (!std::atoi(e)) fill16_shift_ = 0;
+  const int R = variant_.R;
   Batch cur{0, 0, 0, 0, 0, 0, 0};
   std::vector<size_t> ends;
   if (chunk_ends) ends = *chunk_ends;
@@ -404,15 +437,15 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     const TaskIJ &tk = tasks_[t];
     if (tk.i < 0 || tk.i >= pack_->k || tk.j < 0 || tk.j >= pack_->k) throw std::runtime_error("task index out of range");
     const int m = pack_->len[tk.i], n = pack_->len[tk.j];
-    maxlen = std::max<int64_t>(maxlen, std::max(m, n));
     // an empty sequence (undefined in the parallel reference: ceil(0/0) tile size at
     // submit/xuliny-seqalkway.cpp:457; the sequential twin :570-663 returns (m+n)*pgap with a
     // pure-tail alignment) has no DP cells: no strips, the traceback only writes the tails
     StripGeom geo = strip_geometry(m, R, mixed_);
     if (m < 1 || n < 1) geo.nstrips = 0, geo.half_last = 0;
     const uint32_t ns = (uint32_t)geo.nstrips;
-    const uint64_t brow_ints = tiles_ ? (uint64_t)(geo.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(n) + 4)
-                                      : 4ull * (uint64_t)macro_cols(n) + 4;
+    uint64_t brow_ints = tiles_ ? (uint64_t)(geo.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(n) + 4)
+                                : 4ull * (uint64_t)macro_cols(n) + 4;
+    if (fill16_shift_) brow_ints += pair_base_log_ints(ns, n);  // base logs of the strip pairs, behind the kept rows
     // directions, or (tile mode) the column checkpoints [nq / CKQ][rows padded to the strips]
     const uint64_t db = tiles_ ? (uint64_t)(macro_cols(n) / CKQ) * geo.mpad * 4 + 32
                                : (uint64_t)ns * strip_dir_bytes(n, R);
@@ -445,19 +478,8 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     SEQALK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     chunk_ev_.push_back(e);
   }
-  // fast path needs non-negative penalties and scores far from int32 overflow
-  // (|H'| <= 2*max(pxy,pgap)*(m+n)); anything else takes the exact-select kernel.
-  const int64_t pmax = std::max<int64_t>(std::max(pxy, pgap), 1);
-  bool general = pxy < 0 || pgap < 0 || pmax * 4 * maxlen >= (1ll << 29);
-  if (const char *e = std::getenv("SEQALK_FORCE_GENERAL"))
-    if (std::atoi(e)) general = true;
-  // cost table (PRMT) needs <= 4 letters and both shifted costs in a signed byte
-  bool table = pack_->nletters <= 4 && 2 * (int64_t)pgap <= 127 && (int64_t)pxy - 2 * (int64_t)pgap <= 127 &&
-               (int64_t)pxy - 2 * (int64_t)pgap >= -128;
-  if (const char *e = std::getenv("SEQALK_FILL_TAB"))
-    if (!std::atoi(e)) table = false;
-  variant_.mode = general ? MODE_GENERAL : (table ? MODE_TAB : MODE_CMP);
   stats_.tile_mode = tiles_ ? 1 : 0;
+  stats_.fill_packed16 = fill16_shift_ ? 1 : 0;
   stats_.fill_rows_per_lane = (uint32_t)variant_.R;
   // buffer sizes: the largest batch decides, so that run() never reallocates mid-job
   need_ = Batch{0, 0, 0, 0, 0, 0, 0};
@@ -643,6 +665,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       if (tiles_) {
         dir_off += round_up((uint64_t)(macro_cols(d.n) / CKQ) * d.mpad * 4, 32);  // 256-bit checkpoint stores
         brow_off += (uint64_t)(d.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(d.n) + 4);
+        if (fill16_shift_) brow_off += pair_base_log_ints((uint32_t)d.nstrips, d.n);
       } else {
         dir_off += (uint64_t)d.nstrips * strip_dir_bytes(d.n, R);
         brow_off += 4ull * (uint64_t)macro_cols(d.n) + 4;
@@ -692,17 +715,26 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.dirs = static_cast<uint8_t *>(G.dirs.p);
     fa.pxy = pxy_;
     fa.pgap = pgap_;
+    fa.sel16 = static_cast<const uint8_t *>(sel16_.p);
+    fa.rebase_shift = fill16_shift_;
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 0], st));
-    SEQALK_CUDA(launch_fill(fa, variant_, sm_count_, st));
+    if (fill16_shift_)
+      SEQALK_CUDA(launch_fill16(fa, 16, variant_.minb, sm_count_, st));
+    else
+      SEQALK_CUDA(launch_fill(fa, variant_, sm_count_, st));
     if (n_half) {  // second launch: the 512-row last strips
       FillArgs fh = fa;
       fh.tasks = fa.tasks + n_main;
       fh.ntasks = (uint32_t)n_half;
       fh.counter = fa.counter + 1;
-      FillVariant vh = variant_;
-      vh.R = 16;
-      vh.minb = 0;
-      SEQALK_CUDA(launch_fill(fh, vh, sm_count_, st));
+      if (fill16_shift_) {
+        SEQALK_CUDA(launch_fill16(fh, 8, 0, sm_count_, st));
+      } else {
+        FillVariant vh = variant_;
+        vh.R = 16;
+        vh.minb = 0;
+        SEQALK_CUDA(launch_fill(fh, vh, sm_count_, st));
+      }
       stats_.fill_launches++;
     }
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 1], st));
@@ -728,6 +760,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.brow = fa.brow;
     ta.mode = variant_.mode;
     ta.addmode = variant_.addmode;
+    ta.ck16 = fill16_shift_;
     ta.long_pairs = few_pairs_ ? 1 : 0;
     ta.strip_scan = strip_scan_ ? 1 : 0;
     if (const char *e = std::getenv("SEQALK_TB_LONG")) ta.long_pairs = std::atoi(e) ? 1 : 0;

@@ -59,6 +59,7 @@ struct JobStats {
   double wall_ms = 0;          // host wall time of run()
   uint32_t tile_mode = 0;      // 1: score-only fill + tile-recompute traceback; 0: directions in HBM
   uint32_t fill_rows_per_lane = 0;
+  uint32_t fill_packed16 = 0;  // 1: the 16x2-packed fill (fill16.cu) ran the tile-mode fill
   uint32_t self_checked = 0;   // 1: every penalty was compared on the device with the fill's own dp[m][n]
 };
 
@@ -144,7 +145,7 @@ class DeviceWorker {
   int nslots_ = 2;
   std::vector<Slot> slots_;
   cudaStream_t fill_stream_ = nullptr, post_stream_ = nullptr;
-  DevBuf seq_, codes_;
+  DevBuf seq_, codes_, sel16_, seqmeta_;
   const SeqPack *pack_ = nullptr;
   SeqPack pack_copy_;
   std::vector<TaskIJ> tasks_;
@@ -155,6 +156,7 @@ class DeviceWorker {
   FillVariant variant_;
   bool few_pairs_ = false;  // fewer strips than ~2x the resident warps: wavefront-bound job
   bool mixed_ = false;  // tile mode, R = 32: half-height last strips (second fill launch)
+  int fill16_shift_ = 0;  // > 0: the 16x2-packed fill (fill16.cu) runs the tile-mode fill; value = log2 of its re-base interval
   bool tiles_ = false;  // tile mode: score-only fill + checkpoints, directions recomputed per tile
   Batch need_{0, 0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches
   DevBuf res_pen_, res_dig_;
@@ -165,7 +167,11 @@ class DeviceWorker {
   bool ran_ = false;           // a pass over the planned job has completed since plan()
   bool strip_scan_ = false;    // the input contains '_'
   DevBuf check_;               // self-check counters: [0] mismatches, [1] smallest failing task id
-  void verify_check();         // throws if the device-side fill/traceback cross-check failed
+  void verify_check();
+  uint64_t pair_base_log_ints(uint32_t nstrips, int n) const {
+    // rounded to 4 ints: the next pair's kept rows are read and written as int4
+    return ((uint64_t)nstrips * (uint64_t)base_log_entries(macro_cols(n), fill16_shift_) + 3) / 4 * 4;
+  }         // throws if the device-side fill/traceback cross-check failed
   std::vector<size_t> chunk_batch_;  // chunk c = batches [chunk_batch_[c], chunk_batch_[c+1])
   std::vector<cudaEvent_t> chunk_ev_;  // results of chunk c are in the result arrays
   std::thread async_thread_;

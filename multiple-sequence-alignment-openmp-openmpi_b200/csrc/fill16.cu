@@ -1,0 +1,390 @@
+// fill16.cu — the score-only fill of the tile mode with TWO DP cells per register (16x2 SIMD),
+// hand-written for sm_100a.  Same role and same results as fill_kernel<.., EMIT = false> in
+// fill.cu (reference: the DP recurrence of getMinimumPenalty2, submit/xuliny-seqalkway.cpp:462-491,
+// sequential twin :594-609); used when the input has <= 4 letters and the gap penalty is small
+// enough for 16-bit relative scores (fill16_usable).
+//
+// Why: the 32-bit fill needs IDP.4A + VIMNMX3 per cell, each reading three different registers; the
+// SM sub-partition's register file delivers ~2 operands per clock, which caps that instruction mix
+// at IPC ~0.63 (profiles/experiments/issue_rf.cu: 11.2 TCUPS for the bare 32-bit loop, 14.3-15.2
+// for the packed one).  Packing halves the register reads per cell.
+//
+// Decomposition: a "strip pair" = two consecutive strips A, B of 32*RP rows of one pair, swept by
+// ONE warp as a 64-lane virtual warp: virtual lane t (rows of A) lives in the low halves of lane
+// t's registers, virtual lane 32+t (rows of B) in the high halves.  At macro step q physical lane t
+// works on macro column q-t in the low halves and q-t-32 in the high halves.  Lane 31's low half
+// (bottom row of A) feeds lane 0's high half (top row of B) one step later, exactly like every
+// other lane-to-lane hand-off, so a strip pair is one skewed wavefront of 64 x RP rows.
+//
+// Scores are kept in the max domain G = -H' (H' = H - (i+j)*pgap as in fill.cu), relative to a
+// warp-uniform base:  G[i][j] = max3(G[i-1][j-1] + cost, G[i-1][j], G[i][j-1]),
+// cost = 2*pgap on a match, max(0, 2*pgap - pxy) otherwise (a negative mismatch gain can never win:
+// G[i-1][j-1] <= G[i-1][j]).  Per register (two cells):
+//     PRMT        cost pair  = bytes [tabA[r][yA], 0, tabB[r][yB], 0]     (ALU pipe)
+//     IMAD        t = diag + cost pair   (plain 32-bit add: halves never carry) (FMA pipe)
+//     VIMNMX3.U16x2   v = max3(up, left, t)                               (ALU pipe)
+// A half that has not started or is past its last column runs with a null selector (cost 0): it
+// keeps the boundary value 0 resp. copies its last column (G is monotone), so every lane executes
+// every step unconditionally — no per-lane activity branch.  Rows past m have an all-zero table and
+// copy row m (see row_operand in fill_core.cuh): the pair's last kept row carries H'[m][.].
+//
+// 16-bit range: at any step all values of a strip pair lie within 2*pgap*(256 + 64*RP) of each
+// other; every K = 2^rebase_shift steps the warp subtracts the smallest value it holds from all of
+// them (base += delta) and logs the base, so relative scores stay below 65536.
+//
+// What goes to HBM (same places as the 32-bit fill, so traceback_tiles.cu differs only in how it
+// reads a tile's left edge):
+//   * kept rows (every TILE_ROWS DP rows): absolute int32 H', converted with IDP.2A — also the
+//     hand-off row to the next strip pair and the carrier of the corner H'[m][n];
+//   * column checkpoints (every CKQ macro columns): the packed registers as they are; per
+//     checkpoint two images [low halves valid | high halves valid] of mpad/2 words, since the two
+//     halves reach a checkpoint column 32 steps apart; the traceback unpacks with the logged base.
+#include <algorithm>
+
+#include "fill_core.cuh"
+
+namespace seqalk {
+
+namespace {
+
+constexpr int F16_THREADS = 128;
+static_assert(CKQ == 64, "the two halves of a register reach checkpoint columns 32 steps apart");
+constexpr unsigned SEL_NULL = 0xCC88CC88u;  // both columns of a selector word: cost 0 in both halves
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned c) {
+  unsigned d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// c - low / high 16 bits of a (IDP.2A: a = two unsigned halves, b = signed bytes -1 / 0)
+__device__ __forceinline__ int sub_lo16(int c, unsigned a) {
+  int d;
+  asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0x000000ffu), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int sub_hi16(int c, unsigned a) {
+  int d;
+  asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0x0000ff00u), "r"(c));
+  return d;
+}
+
+// One lane's RP x 4 block of packed cells (column-major).  sel01 / sel23: the selector words of
+// the macro column (16 bits per DP column).
+template <int RP>
+__device__ __forceinline__ void macro_step16(unsigned (&h)[RP], unsigned &dg, const unsigned (&tl)[RP],
+                                             const unsigned (&th)[RP], const unsigned (&up_in)[4], unsigned sel01,
+                                             unsigned sel23, unsigned one, unsigned (&outv)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const unsigned w = c < 2 ? sel01 : sel23;
+    const unsigned sel = (c & 1) ? (w >> 16) : w;  // PRMT reads the low 16 bits of its selector
+    unsigned diag = dg, up = up_in[c];
+    dg = up;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+      const unsigned left = h[r];
+      const unsigned cost = prmt(tl[r], th[r], sel);
+      unsigned t;
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(diag), "r"(one), "r"(cost));
+      const unsigned v = __vimax3_u16x2(up, left, t);
+      diag = left;
+      up = v;
+      h[r] = v;
+    }
+    outv[c] = up;
+  }
+}
+
+// Cost table of one DP row in the max domain: byte q = gain of the row's letter against letter q.
+__device__ __forceinline__ unsigned row_table16(bool inside, unsigned ch, unsigned cm, unsigned cx) {
+  return inside ? ((cx * 0x01010101u) ^ ((cm ^ cx) << (ch & 24u))) : 0u;  // ch = 8 * letter code
+}
+
+template <int RP>
+__device__ __forceinline__ void process_strip_pair(const FillArgs &a, const PairDesc &P, const int s,
+                                                   const int row_base, const int lane, uint2 *ring_sel,
+                                                   int4 *ring_top) {
+  const unsigned FULL = 0xffffffffu;
+  const int m = P.m, n = P.n;
+  const int nq = (n + 3) >> 2;
+  const int nsteps = nq + 63;
+  const bool first = (s == 0), last = (s == P.nstrips - 1);
+  const int KS = a.rebase_shift;
+  const unsigned one = (unsigned)a.one;
+  const unsigned cm = (unsigned)(2 * a.pgap), cx = (unsigned)max(0, 2 * a.pgap - a.pxy);
+
+  // ---- this lane's rows: RP of strip A (low halves), RP of strip B (high halves)
+  const int rowA0 = row_base + lane * RP, rowB0 = rowA0 + 32 * RP;
+  unsigned tl[RP], th[RP];
+  {
+    const uint8_t *__restrict__ xs = a.codes + P.x_off;  // zero padded far beyond m (engine.cu)
+    unsigned wa[RP / 4], wb[RP / 4];
+    static_assert(RP == 16 || RP == 8, "rows per half lane");
+    if constexpr (RP == 16) {
+      const uint4 va = rowA0 < m ? __ldg(reinterpret_cast<const uint4 *>(xs + rowA0)) : make_uint4(0, 0, 0, 0);
+      const uint4 vb = rowB0 < m ? __ldg(reinterpret_cast<const uint4 *>(xs + rowB0)) : make_uint4(0, 0, 0, 0);
+      wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
+      wb[0] = vb.x; wb[1] = vb.y; wb[2] = vb.z; wb[3] = vb.w;
+    } else {
+      const uint2 va = rowA0 < m ? __ldg(reinterpret_cast<const uint2 *>(xs + rowA0)) : make_uint2(0, 0);
+      const uint2 vb = rowB0 < m ? __ldg(reinterpret_cast<const uint2 *>(xs + rowB0)) : make_uint2(0, 0);
+      wa[0] = va.x; wa[1] = va.y;
+      wb[0] = vb.x; wb[1] = vb.y;
+    }
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+      tl[r] = row_table16(rowA0 + r < m, (wa[r >> 2] >> (8 * (r & 3))) & 0xffu, cm, cx);
+      th[r] = row_table16(rowB0 + r < m, (wb[r >> 2] >> (8 * (r & 3))) & 0xffu, cm, cx);
+    }
+  }
+
+  // ---- where things go
+  const uint64_t bstride = (uint64_t)(4 * nq + 4);
+  int32_t *bbase = a.brow + P.brow_off;
+  const int4 *__restrict__ brow_rd =
+      reinterpret_cast<const int4 *>(bbase + (uint64_t)(first ? 0 : row_base / TILE_ROWS - 1) * bstride);
+  const bool keep = ((lane * RP + RP) & (TILE_ROWS - 1)) == 0;  // this lane's bottom rows are kept rows
+  int4 *__restrict__ keepA = reinterpret_cast<int4 *>(bbase + (uint64_t)(rowA0 / TILE_ROWS) * bstride);
+  int4 *__restrict__ keepB = reinterpret_cast<int4 *>(bbase + (uint64_t)(rowB0 / TILE_ROWS) * bstride);
+  // column checkpoints: image (k, half) = mpad/2 packed words; this lane's RP words start at
+  // row_base/2 + lane*RP (strip pairs are laid out one after the other)
+  const uint64_t halfwords = (uint64_t)P.mpad / 2;
+  uint32_t *__restrict__ ck = reinterpret_cast<uint32_t *>(a.dirs + P.dir_off) + (uint64_t)(row_base / 2 + lane * RP);
+  // base log of this strip pair, behind the pair's kept rows
+  const int nbl = base_log_entries(nq, KS);
+  int32_t *blog = bbase + (uint64_t)(P.mpad / TILE_ROWS) * bstride + (uint64_t)s * nbl;
+  const uint2 *__restrict__ selstream = reinterpret_cast<const uint2 *>(a.sel16 + 2 * (uint64_t)P.y_off);
+  const unsigned *prev_progress = a.progress + P.strip0 + (first ? 0 : s - 1);
+  unsigned *my_progress = a.progress + P.strip0 + s;
+
+  unsigned h[RP];
+#pragma unroll
+  for (int r = 0; r < RP; ++r) h[r] = 0u;
+  unsigned dg = 0u, outv[4] = {0u, 0u, 0u, 0u};
+  int negbase = 0;  // -(base): absolute G = relative - negbase, H' = negbase - relative
+  const unsigned merge = lane == 0 ? 0x1054u : 0x3210u;  // lane 0: low half <- top row, high half <- lane 31's low half
+  const int src_lane = (lane + 31) & 31;
+  int avail = first ? nq : 0;
+  if (lane == 0) blog[0] = 0;
+
+  __syncwarp();
+  ring_sel[32 + lane] = make_uint2(SEL_NULL, SEL_NULL);  // stream entries -31..-1: halves not started yet
+
+  const int nblocks = (nsteps + 31) >> 5;
+  for (int blk = 0; blk < nblocks; ++blk) {
+    // ---- stage the block's 32 stream entries: selector words of macro column e (low halves) /
+    // e - 32 (high halves), and the predecessor's bottom row at macro column e (lane 0's top row)
+    const int e = blk * 32 + lane;
+    if (!first) {
+      const int need = min(nq, blk * 32 + 32);
+      if (avail < need) {
+        // relaxed polls (an acquire load invalidates the SM's L1), one acquire once the value is there
+        unsigned ns = 32;
+        for (;;) {
+          unsigned v = 0;
+          if (lane == 0) v = ld_relaxed_u32(prev_progress);
+          v = __shfl_sync(FULL, v, 0);
+          if ((int)v >= need) break;
+          __nanosleep(ns);
+          if (ns < 2048) ns *= 2;
+        }
+        unsigned v = 0;
+        if (lane == 0) v = ld_acquire_u32(prev_progress);
+        avail = (int)__shfl_sync(FULL, v, 0);
+      }
+    }
+    const uint2 sv = e < nq + 64 ? __ldg(selstream + e) : make_uint2(SEL_NULL, SEL_NULL);
+    int4 tv = make_int4(0, 0, 0, 0);
+    if (!first) {
+      if (e < nq) {
+        tv = __ldcg(brow_rd + e);
+      } else {  // past the last column: keep copying it (the halves keep running with cost 0)
+        const int lastv = __ldcg(reinterpret_cast<const int *>(brow_rd) + 4 * nq - 1);
+        tv = make_int4(lastv, lastv, lastv, lastv);
+      }
+    }
+    __syncwarp();
+    ring_sel[(blk & 1) * 32 + lane] = sv;
+    ring_top[lane] = tv;
+    __syncwarp();
+
+    const int send = min(32, nsteps - blk * 32);
+    for (int st = 0; st < send; ++st) {
+      const int q = blk * 32 + st;
+      // ---- re-base (warp-uniform): subtract the smallest value any lane holds
+      if (q > 0 && (q & ((1 << KS) - 1)) == 0) {
+        unsigned mn = __vminu2(dg, outv[0]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mn = __vminu2(mn, __shfl_xor_sync(FULL, mn, d));
+        const unsigned delta = min(mn & 0xffffu, mn >> 16);
+        const unsigned dd = delta * 0x10001u;
+#pragma unroll
+        for (int r = 0; r < RP; ++r) h[r] -= dd;  // both halves >= delta: no borrow across
+#pragma unroll
+        for (int c = 0; c < 4; ++c) outv[c] -= dd;
+        dg -= dd;
+        negbase -= (int)delta;
+        if (lane == 0) blog[q >> KS] = -negbase;
+      }
+      // ---- neighbours: every lane takes the bottom rows of the lane above (both halves); lane 0
+      // takes lane 31's low half (bottom row of strip A) as its high half and the staged top row
+      // (absolute H' -> relative G) as its low half
+      const int4 tv4 = ring_top[st];
+      unsigned up_in[4];
+      up_in[0] = prmt(__shfl_sync(FULL, outv[0], src_lane), (unsigned)(negbase - tv4.x), merge);
+      up_in[1] = prmt(__shfl_sync(FULL, outv[1], src_lane), (unsigned)(negbase - tv4.y), merge);
+      up_in[2] = prmt(__shfl_sync(FULL, outv[2], src_lane), (unsigned)(negbase - tv4.z), merge);
+      up_in[3] = prmt(__shfl_sync(FULL, outv[3], src_lane), (unsigned)(negbase - tv4.w), merge);
+      const uint2 sw = ring_sel[(q - lane) & 63];
+      macro_step16<RP>(h, dg, tl, th, up_in, sw.x, sw.y, one, outv);
+
+      const int qcA = q - lane, qcB = qcA - 32;
+      // ---- kept rows (absolute H'): tile traceback, hand-off to the next strip pair, corner
+      if (keep) {
+        if (qcA >= 0 && qcA < nq)
+          keepA[qcA] = make_int4(sub_lo16(negbase, outv[0]), sub_lo16(negbase, outv[1]), sub_lo16(negbase, outv[2]),
+                                 sub_lo16(negbase, outv[3]));
+        if (qcB >= 0 && qcB < nq)
+          keepB[qcB] = make_int4(sub_hi16(negbase, outv[0]), sub_hi16(negbase, outv[1]), sub_hi16(negbase, outv[2]),
+                                 sub_hi16(negbase, outv[3]));
+      }
+      // ---- column checkpoints: the packed registers as they are (one lane at a time takes this)
+      if (((qcA + 1) & 31) == 0) {
+        const int ckcol = (qcA + 1) >> 5;  // even: the low halves are at a checkpoint column, odd: the high halves
+        const int half = ckcol & 1;
+        const int k = (ckcol >> 1) - 1;  // checkpoint index of that half's column
+        const int qc = half ? qcB : qcA;
+        if (k >= 0 && qc >= 0 && qc < nq) {
+          uint32_t *dst = ck + ((uint64_t)k * 2 + half) * halfwords;
+#pragma unroll
+          for (int r8 = 0; r8 < RP / 8; ++r8)
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * r8), "r"(h[8 * r8]),
+                         "r"(h[8 * r8 + 1]), "r"(h[8 * r8 + 2]), "r"(h[8 * r8 + 3]), "r"(h[8 * r8 + 4]),
+                         "r"(h[8 * r8 + 5]), "r"(h[8 * r8 + 6]), "r"(h[8 * r8 + 7])
+                         : "memory");
+        }
+      }
+      // ---- publish the progress of the bottom row (virtual lane 63)
+      if (!last) {
+        const int done = min(nq, q - 62);
+        if (done > 0 && (done == nq || (done & ((1 << a.publish_shift) - 1)) == 0)) {
+          if (q - 62 <= nq && lane == 31) st_release_u32(my_progress, (unsigned)done);
+        }
+      }
+    }
+  }
+}
+
+template <int RP, int MINB>
+__global__ void __launch_bounds__(F16_THREADS, MINB) fill16_kernel(const FillArgs a) {
+  __shared__ uint2 s_sel[F16_THREADS / 32][64];
+  __shared__ int4 s_top[F16_THREADS / 32][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(a.counter, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.ntasks) break;
+    const StripTask task = a.tasks[t];
+    const PairDesc P = a.pairs[task.pair];
+    const int s = (int)task.strip;
+    // main launch: strip pairs of 64*16 = 1024 rows; a pair's 512-row last strip pair (see
+    // strip_geometry) runs in the second launch with 8 rows per half lane
+    const int row_base = (P.half_last && s == P.nstrips - 1) ? (int)P.mpad - 64 * RP : s * (64 * RP);
+    process_strip_pair<RP>(a, P, s, row_base, lane, s_sel[warp], s_top[warp]);
+  }
+}
+
+// ---- selector streams, one per sequence (built once per load): entry e = two words, 16 bits per
+// DP column c of macro column e: nibbles [code of y[4e+c] | 8, 8, 4 + code of y[4(e-32)+c] | 0xC, 0xC]
+__global__ void build_sel16_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ sel16,
+                                   const uint32_t *__restrict__ off, const int32_t *__restrict__ len, int k) {
+  const int seq = blockIdx.y;
+  if (seq >= k) return;
+  const int n = len[seq], nq = (n + 3) >> 2;
+  const uint8_t *y = codes + off[seq];
+  uint2 *out = reinterpret_cast<uint2 *>(sel16 + 2 * (uint64_t)off[seq]);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nq + 64; e += gridDim.x * blockDim.x) {
+    unsigned w[2] = {0u, 0u};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ja = 4 * e + c, jb = 4 * (e - 32) + c;
+      const unsigned lo = (ja < n) ? (unsigned)(y[ja] >> 3) : 8u;
+      const unsigned hi = (jb >= 0 && jb < n) ? 4u + (unsigned)(y[jb] >> 3) : 0xCu;
+      const unsigned s16 = 0xC080u | lo | (hi << 8);
+      w[c >> 1] |= s16 << (16 * (c & 1));
+    }
+    out[e] = make_uint2(w[0], w[1]);
+  }
+}
+
+typedef void (*Fill16Ptr)(const FillArgs);
+Fill16Ptr pick16(int rp, int minb) {
+  if (rp == 16) {
+    if (minb == 4) return fill16_kernel<16, 4>;
+    if (minb == 6) return fill16_kernel<16, 6>;
+    if (minb == 7) return fill16_kernel<16, 7>;
+    return fill16_kernel<16, 5>;
+  }
+  if (rp == 8) return fill16_kernel<8, 8>;
+  return nullptr;
+}
+
+}  // namespace
+
+// 16-bit relative scores need: byte-sized gains, and the spread of a strip pair plus the growth
+// over one re-base interval below 2^16.  Returns the re-base interval's log2 (>= 6), or 0.
+int fill16_rebase_shift(int pxy, int pgap) {
+  if (pxy < 0 || pgap < 0 || 2 * (int64_t)pgap > 127) return 0;
+  if (pgap == 0) return 10;
+  // values within 2*pgap*(256 + 64*16) of each other + 2*pgap*4 per step + 1024 steps of slack for halves
+  // that have finished
+  for (int ks = 10; ks >= 6; --ks)
+    if (2ll * pgap * (4ll * (1 << ks) + 256 + 64 * 16 + 4 * 256) <= 65535 - 2ll * pgap) return ks;
+  return 0;
+}
+
+cudaError_t launch_build_sel16(const uint8_t *codes, uint8_t *sel16, const uint32_t *off_dev, const int32_t *len_dev,
+                               int k, int maxlen, cudaStream_t stream) {
+  if (k == 0) return cudaSuccess;
+  const int entries = ((maxlen + 3) >> 2) + 64;
+  dim3 grid((unsigned)std::min(64, (entries + 255) / 256), (unsigned)k);
+  build_sel16_kernel<<<grid, 256, 0, stream>>>(codes, sel16, off_dev, len_dev, k);
+  return cudaGetLastError();
+}
+
+int fill16_blocks_per_sm(int rp, int minb) {
+  Fill16Ptr k = pick16(rp, minb);
+  if (!k) return 0;
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, F16_THREADS, 0);
+  return nb;
+}
+
+cudaError_t launch_fill16(const FillArgs &args, int rp, int minb, int sm_count, cudaStream_t stream) {
+  if (args.ntasks == 0) return cudaSuccess;
+  Fill16Ptr k = pick16(rp, minb);
+  if (!k) return cudaErrorInvalidValue;
+  const int nb = fill16_blocks_per_sm(rp, minb);
+  if (nb < 1) return cudaErrorLaunchOutOfResources;
+  long long want = ((long long)args.ntasks + (F16_THREADS / 32) - 1) / (F16_THREADS / 32);
+  long long grid = (long long)sm_count * nb;
+  if (grid > want) grid = want;
+  k<<<(unsigned)grid, F16_THREADS, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace seqalk

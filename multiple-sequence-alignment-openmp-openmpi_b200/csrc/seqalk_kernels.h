@@ -33,6 +33,10 @@ constexpr int TRACEBACK_THREADS = 32;
 constexpr int DIGEST_THREADS = 64;
 // bytes that may be read past the end of the packed sequence / alignment buffers
 constexpr int BUFFER_SLACK = 64;
+// zero bytes behind every sequence: the fill reads y in 4-byte words and x in 16-byte words, and the
+// selector stream of a sequence (fill16.cu: 8 bytes per macro column, 64 extra entries) lives at twice
+// the sequence's offset in a buffer twice as large
+constexpr int SEQ_PAD = 272;
 
 struct FillArgs {
   const uint8_t *seq;       // packed sequences (each 16 B aligned, zero padded)
@@ -47,6 +51,9 @@ struct FillArgs {
   int32_t pxy, pgap;
   int32_t one;              // == 1, opaque to the compiler (see add_i in fill.cu)
   int32_t publish_shift;    // log2 of the publication interval in macro columns
+  // 16x2-packed fill (fill16.cu) only:
+  const uint8_t *sel16;     // selector streams, one per sequence, at byte offset 2 * (offset of the sequence)
+  int32_t rebase_shift;     // log2 of the re-base interval in macro steps
 };
 
 struct TracebackArgs {
@@ -65,6 +72,8 @@ struct TracebackArgs {
                             // satisfies dp[cell] = dp[predecessor] + step cost, and dp[i][0] = i*pgap)
   int32_t pxy, pgap;
   int32_t R;                // rows per lane the fill used (direction layout)
+  int32_t ck16;             // tile mode: 0 = int32 column checkpoints (fill.cu); else the 16x2-packed fill's
+                            // checkpoints (fill16.cu), value = log2 of its re-base interval
   int32_t strip_scan;       // 1: the input contains '_' (the gap character): apply the reference's
                             // strip rule literally (submit/xuliny-seqalkway.cpp:191-202): the alignment
                             // starts after the LAST column holding '_' in both strings
@@ -111,6 +120,14 @@ struct ScoreArgs {
 };
 
 cudaError_t launch_fill(const FillArgs &args, const FillVariant &v, int sm_count, cudaStream_t stream);
+// 16x2-packed score-only fill: rp = rows per half lane (16: strip pairs of 1024 rows, 8: 512 rows)
+cudaError_t launch_fill16(const FillArgs &args, int rp, int minb, int sm_count, cudaStream_t stream);
+int fill16_blocks_per_sm(int rp, int minb);
+int fill16_rebase_shift(int pxy, int pgap);  // 0: penalties do not fit the 16-bit scheme
+cudaError_t launch_build_sel16(const uint8_t *codes, uint8_t *sel16, const uint32_t *off_dev, const int32_t *len_dev,
+                               int k, int maxlen, cudaStream_t stream);
+// entries of a strip pair's base log for a pair with nq macro columns
+__host__ __device__ inline int base_log_entries(int nq, int rebase_shift) { return ((nq + 64) >> rebase_shift) + 1; }
 int fill_blocks_per_sm(const FillVariant &v);
 cudaError_t launch_traceback(const TracebackArgs &args, cudaStream_t stream);
 cudaError_t launch_traceback_tiles(const TracebackArgs &args, cudaStream_t stream);

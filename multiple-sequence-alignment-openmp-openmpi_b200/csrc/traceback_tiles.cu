@@ -39,6 +39,10 @@ struct TileCtx {
   const uint8_t *xop;          // row operands: letter codes (MODE_TAB) or raw characters
   const unsigned *yw32;        // y as 4-byte words (codes or raw)
   const int32_t *brow, *ck;    // kept rows, column checkpoints
+  // 16x2-packed column checkpoints (fill16.cu), ck16 = log2 of the fill's re-base interval (0: int32
+  // checkpoints): image (k, half) of mpad/2 packed words, relative to the base the fill logged
+  int ck16;
+  int nstrips, half_last;
 };
 
 template <int MODE>
@@ -58,6 +62,9 @@ __device__ __forceinline__ TileCtx make_ctx(const TracebackArgs &a, const PairDe
   T.yw32 = reinterpret_cast<const unsigned *>(opbase + P.y_off);
   T.brow = a.brow + P.brow_off;
   T.ck = reinterpret_cast<const int32_t *>(a.dirs + P.dir_off);
+  T.ck16 = a.ck16;
+  T.nstrips = P.nstrips;
+  T.half_last = (int)P.half_last;
   return T;
 }
 
@@ -92,7 +99,34 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
       const int ch = inside ? (int)T.xop[r0 + r] : 0;
       xc[r] = row_operand<MODE>(inside, ch, r, T.A, T.B);
     }
-    if (cb > 0) {  // left edge = column checkpoint cb-1
+    if (cb > 0 && T.ck16) {
+      // left edge from the packed fill's checkpoint cb-1.  Row r0 lies in the strip pair starting
+      // at row sp0 (1024 rows; the pair's last one 512 rows if half_last), in its first half A (low
+      // 16 bits) or second half B (high 16 bits), on virtual lane vl of 64; that lane reached the
+      // checkpoint column (macro column 64*cb - 1) at macro step 64*cb - 1 + vl: the base logged
+      // for that step makes the value absolute:  H' = -(base + relative).
+      const int tail0 = (int)T.mpad - 512;
+      const bool in_half = T.half_last && r0 >= tail0;
+      const int sp_rows = in_half ? 512 : 1024;
+      const int s = in_half ? T.nstrips - 1 : r0 >> 10;
+      const int sp0 = in_half ? tail0 : (r0 >> 10) << 10;
+      const int rem = r0 - sp0;
+      const int half = rem >= (sp_rows >> 1) ? 1 : 0;
+      const int vl = rem / (sp_rows >> 6);
+      const int step = CKQ * cb - 1 + vl;
+      const int32_t *blog = T.brow + (uint64_t)(T.mpad / TILE_ROWS) * T.bstride +
+                            (uint64_t)s * (uint64_t)base_log_entries(T.nq, T.ck16);
+      const int base = __ldcg(blog + (step >> T.ck16));
+      const uint32_t *img = reinterpret_cast<const uint32_t *>(T.ck) + ((uint64_t)(cb - 1) * 2 + half) * (T.mpad / 2);
+      const uint4 *src = reinterpret_cast<const uint4 *>(img + (sp0 >> 1) + (rem - half * (sp_rows >> 1)));
+#pragma unroll
+      for (int r4 = 0; r4 < RT / 4; ++r4) {
+        const uint4 v = __ldcg(src + r4);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) h[4 * r4 + r] = -(base + (int)(half ? (w[r] >> 16) : (w[r] & 0xffffu)));
+      }
+    } else if (cb > 0) {  // left edge = column checkpoint cb-1
       const int4 *src = reinterpret_cast<const int4 *>(T.ck + (uint64_t)(cb - 1) * T.mpad + (uint64_t)r0);
 #pragma unroll
       for (int r4 = 0; r4 < RT / 4; ++r4) {
