@@ -99,7 +99,7 @@ __device__ __forceinline__ void macro_step16(unsigned (&h)[RP], unsigned &dg, co
       const unsigned cost = prmt(tl[r], th[r], sel);
       unsigned t;
       asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(diag), "r"(one), "r"(cost));
-      const unsigned v = __vimax3_u16x2(up, left, t);
+      const unsigned v = __vimax3_u16x2(left, up, t);  // left first: same operand slot as the next row's diag
       diag = left;
       up = v;
       h[r] = v;
@@ -179,17 +179,40 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
   const int src_lane = (lane + 31) & 31;
   int avail = first ? nq : 0;
   if (lane == 0) blog[0] = 0;
+  const unsigned nq_keep = keep ? (unsigned)nq : 0u;  // store predicate: (unsigned)column < nq_keep
+  // The selector ring holds every entry twice, 64 slots apart: entry q - lane is read at slot
+  // (q & 63) + 64 - lane without a wrap-around (a lane-constant address plus a uniform offset).
+  const uint8_t *sel_rd = reinterpret_cast<const uint8_t *>(ring_sel + 64 - lane);
+  const uint8_t *top_rd = reinterpret_cast<const uint8_t *>(ring_top);
+  int qcA = -lane;  // macro column of the low halves at step q
 
   __syncwarp();
-  ring_sel[32 + lane] = make_uint2(SEL_NULL, SEL_NULL);  // stream entries -31..-1: halves not started yet
+  ring_sel[32 + lane] = ring_sel[96 + lane] = make_uint2(SEL_NULL, SEL_NULL);  // entries -31..-1: halves not started yet
 
   const int nblocks = (nsteps + 31) >> 5;
   for (int blk = 0; blk < nblocks; ++blk) {
+    const int q0 = blk * 32;
+    // ---- re-base (block starts that are multiples of the interval): subtract the smallest value
+    // any lane holds from everything the warp holds
+    if (q0 > 0 && (q0 & ((1 << KS) - 1)) == 0) {
+      unsigned mn = __vminu2(dg, outv[0]);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) mn = __vminu2(mn, __shfl_xor_sync(FULL, mn, d));
+      const unsigned delta = min(mn & 0xffffu, mn >> 16);
+      const unsigned dd = delta * 0x10001u;
+#pragma unroll
+      for (int r = 0; r < RP; ++r) h[r] -= dd;  // both halves >= delta: no borrow across
+#pragma unroll
+      for (int c = 0; c < 4; ++c) outv[c] -= dd;
+      dg -= dd;
+      negbase -= (int)delta;
+      if (lane == 0) blog[q0 >> KS] = -negbase;
+    }
     // ---- stage the block's 32 stream entries: selector words of macro column e (low halves) /
     // e - 32 (high halves), and the predecessor's bottom row at macro column e (lane 0's top row)
-    const int e = blk * 32 + lane;
+    const int e = q0 + lane;
     if (!first) {
-      const int need = min(nq, blk * 32 + 32);
+      const int need = min(nq, q0 + 32);
       if (avail < need) {
         // relaxed polls (an acquire load invalidates the SM's L1), one acquire once the value is there
         unsigned ns = 32;
@@ -217,56 +240,47 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
       }
     }
     __syncwarp();
-    ring_sel[(blk & 1) * 32 + lane] = sv;
-    ring_top[lane] = tv;
+    ring_sel[(blk & 1) * 32 + lane] = ring_sel[(blk & 1) * 32 + 64 + lane] = sv;
+    // absolute H' -> relative G (the base only changes at block starts)
+    ring_top[lane] = make_int4(negbase - tv.x, negbase - tv.y, negbase - tv.z, negbase - tv.w);
     __syncwarp();
 
-    const int send = min(32, nsteps - blk * 32);
+    const int send = min(32, nsteps - q0);
+#pragma unroll 1  // keeps the rows in fixed registers (vector stores of the checkpoints without moves)
     for (int st = 0; st < send; ++st) {
-      const int q = blk * 32 + st;
-      // ---- re-base (warp-uniform): subtract the smallest value any lane holds
-      if (q > 0 && (q & ((1 << KS) - 1)) == 0) {
-        unsigned mn = __vminu2(dg, outv[0]);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mn = __vminu2(mn, __shfl_xor_sync(FULL, mn, d));
-        const unsigned delta = min(mn & 0xffffu, mn >> 16);
-        const unsigned dd = delta * 0x10001u;
-#pragma unroll
-        for (int r = 0; r < RP; ++r) h[r] -= dd;  // both halves >= delta: no borrow across
-#pragma unroll
-        for (int c = 0; c < 4; ++c) outv[c] -= dd;
-        dg -= dd;
-        negbase -= (int)delta;
-        if (lane == 0) blog[q >> KS] = -negbase;
-      }
       // ---- neighbours: every lane takes the bottom rows of the lane above (both halves); lane 0
-      // takes lane 31's low half (bottom row of strip A) as its high half and the staged top row
-      // (absolute H' -> relative G) as its low half
-      const int4 tv4 = ring_top[st];
+      // takes lane 31's low half (bottom row of strip A) as its high half and the staged top row as
+      // its low half
+      const int4 tv4 = *reinterpret_cast<const int4 *>(top_rd + 16 * st);
       unsigned up_in[4];
-      up_in[0] = prmt(__shfl_sync(FULL, outv[0], src_lane), (unsigned)(negbase - tv4.x), merge);
-      up_in[1] = prmt(__shfl_sync(FULL, outv[1], src_lane), (unsigned)(negbase - tv4.y), merge);
-      up_in[2] = prmt(__shfl_sync(FULL, outv[2], src_lane), (unsigned)(negbase - tv4.z), merge);
-      up_in[3] = prmt(__shfl_sync(FULL, outv[3], src_lane), (unsigned)(negbase - tv4.w), merge);
-      const uint2 sw = ring_sel[(q - lane) & 63];
+      up_in[0] = prmt(__shfl_sync(FULL, outv[0], src_lane), (unsigned)tv4.x, merge);
+      up_in[1] = prmt(__shfl_sync(FULL, outv[1], src_lane), (unsigned)tv4.y, merge);
+      up_in[2] = prmt(__shfl_sync(FULL, outv[2], src_lane), (unsigned)tv4.z, merge);
+      up_in[3] = prmt(__shfl_sync(FULL, outv[3], src_lane), (unsigned)tv4.w, merge);
+      const uint2 sw = *reinterpret_cast<const uint2 *>(sel_rd + 8 * ((q0 + st) & 63));
       macro_step16<RP>(h, dg, tl, th, up_in, sw.x, sw.y, one, outv);
 
-      const int qcA = q - lane, qcB = qcA - 32;
-      // ---- kept rows (absolute H'): tile traceback, hand-off to the next strip pair, corner
-      if (keep) {
-        if (qcA >= 0 && qcA < nq)
-          keepA[qcA] = make_int4(sub_lo16(negbase, outv[0]), sub_lo16(negbase, outv[1]), sub_lo16(negbase, outv[2]),
-                                 sub_lo16(negbase, outv[3]));
-        if (qcB >= 0 && qcB < nq)
-          keepB[qcB] = make_int4(sub_hi16(negbase, outv[0]), sub_hi16(negbase, outv[1]), sub_hi16(negbase, outv[2]),
-                                 sub_hi16(negbase, outv[3]));
+      // ---- kept rows (absolute H'): tile traceback, hand-off to the next strip pair, corner.
+      // Predicated stores, no branch: the conversions run on the FMA pipe, which has room.
+      {
+        const int qcB = qcA - 32;
+        const int a0 = sub_lo16(negbase, outv[0]), a1 = sub_lo16(negbase, outv[1]), a2 = sub_lo16(negbase, outv[2]),
+                  a3 = sub_lo16(negbase, outv[3]);
+        const int b0 = sub_hi16(negbase, outv[0]), b1 = sub_hi16(negbase, outv[1]), b2 = sub_hi16(negbase, outv[2]),
+                  b3 = sub_hi16(negbase, outv[3]);
+        asm volatile("{.reg .pred p; setp.lt.u32 p, %5, %6; @p st.global.v4.b32 [%0], {%1,%2,%3,%4};}" ::"l"(keepA + qcA),
+                     "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(qcA), "r"(nq_keep)
+                     : "memory");
+        asm volatile("{.reg .pred p; setp.lt.u32 p, %5, %6; @p st.global.v4.b32 [%0], {%1,%2,%3,%4};}" ::"l"(keepB + qcB),
+                     "r"(b0), "r"(b1), "r"(b2), "r"(b3), "r"(qcB), "r"(nq_keep)
+                     : "memory");
       }
       // ---- column checkpoints: the packed registers as they are (one lane at a time takes this)
       if (((qcA + 1) & 31) == 0) {
         const int ckcol = (qcA + 1) >> 5;  // even: the low halves are at a checkpoint column, odd: the high halves
         const int half = ckcol & 1;
         const int k = (ckcol >> 1) - 1;  // checkpoint index of that half's column
-        const int qc = half ? qcB : qcA;
+        const int qc = half ? qcA - 32 : qcA;
         if (k >= 0 && qc >= 0 && qc < nq) {
           uint32_t *dst = ck + ((uint64_t)k * 2 + half) * halfwords;
 #pragma unroll
@@ -277,20 +291,20 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
                          : "memory");
         }
       }
-      // ---- publish the progress of the bottom row (virtual lane 63)
-      if (!last) {
-        const int done = min(nq, q - 62);
-        if (done > 0 && (done == nq || (done & ((1 << a.publish_shift) - 1)) == 0)) {
-          if (q - 62 <= nq && lane == 31) st_release_u32(my_progress, (unsigned)done);
-        }
-      }
+      ++qcA;
+    }
+    // ---- publish the progress of the bottom row (virtual lane 63 = lane 31's high halves), once
+    // per block: the next strip pair consumes it in blocks of 32 columns as well
+    if (!last) {
+      const int done = min(nq, q0 + send - 63);
+      if (done > 0 && lane == 31) st_release_u32(my_progress, (unsigned)done);
     }
   }
 }
 
 template <int RP, int MINB>
 __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_kernel(const FillArgs a) {
-  __shared__ uint2 s_sel[F16_THREADS / 32][64];
+  __shared__ uint2 s_sel[F16_THREADS / 32][128];
   __shared__ int4 s_top[F16_THREADS / 32][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (;;) {
@@ -334,10 +348,11 @@ __global__ void build_sel16_kernel(const uint8_t *__restrict__ codes, uint8_t *_
 typedef void (*Fill16Ptr)(const FillArgs);
 Fill16Ptr pick16(int rp, int minb) {
   if (rp == 16) {
+    // 6 CTAs per SM (<= 80 registers): 161 ms per cfg3 job against 168 (5 CTAs), 173 (4), 180 (7)
     if (minb == 4) return fill16_kernel<16, 4>;
-    if (minb == 6) return fill16_kernel<16, 6>;
+    if (minb == 5) return fill16_kernel<16, 5>;
     if (minb == 7) return fill16_kernel<16, 7>;
-    return fill16_kernel<16, 5>;
+    return fill16_kernel<16, 6>;
   }
   if (rp == 8) return fill16_kernel<8, 8>;
   return nullptr;

@@ -14,6 +14,8 @@
 #define MIN3(r, a, b) asm volatile("{.reg .s32 t; min.s32 t, %0, %1; min.s32 %0, t, %2;}" : "+r"(r) : "r"(a), "r"(b))
 #define DP4A(r, a, b) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b))
 #define MIN2(r, a) asm volatile("min.s32 %0, %0, %1;" : "+r"(r) : "r"(a))
+#define MAX3U(r, a, b) asm volatile("{.reg .b32 t; max.u16x2 t, %0, %1; max.u16x2 %0, t, %2;}" : "+r"(r) : "r"(a), "r"(b))
+#define PRMTD(r, a, b) asm volatile("prmt.b32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b))
 #define MAD1(r, a, one) asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(one))
 
 template <int KIND>
@@ -76,6 +78,35 @@ __global__ void __launch_bounds__(128) opk(int *out, const int *in, int iters, i
           MIN3(q[i], b[i], a[(i + 1) & 7]);
         }
       }
+      if (KIND == 8) {  // VIMNMX3.U16x2, three distinct registers
+#pragma unroll
+        for (int i = 0; i < 8; ++i) MAX3U(r[i], a[i], b[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) MAX3U(q[i], b[(i + 3) & 7], a[(i + 5) & 7]);
+      }
+      if (KIND == 9) {  // the packed fill's mix: PRMT + IMAD + VIMNMX3.U16x2 on independent registers
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          PRMTD(a[i], r[i], b[i]);
+          MAD1(b[i], q[i], one);
+          MAX3U(q[(i + 1) & 7], r[(i + 2) & 7], a[(i + 3) & 7]);
+        }
+      }
+      if (KIND == 11) {  // PRMT with its two table operands shared (per-column tables) + IMAD + VIMNMX3.U16x2
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          asm volatile("prmt.b32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(r[0]), "r"(b[0]));
+          MAD1(b[(i & 3) + 4], q[i], one);
+          MAX3U(q[(i + 1) & 7], r[(i + 2) & 7], a[(i + 3) & 7]);
+        }
+      }
+      if (KIND == 10) {  // PRMT + VIMNMX3.U16x2 (ALU pipe only)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          PRMTD(a[i], r[i], b[i]);
+          MAX3U(q[i], r[(i + 2) & 7], b[(i + 3) & 7]);
+        }
+      }
       if (KIND == 7) {  // VIMNMX3 with ONE shared source
 #pragma unroll
         for (int i = 0; i < 8; ++i) MIN3(r[i], a[0], b[i]);
@@ -108,7 +139,8 @@ void run_op(const char *name, int ctas_per_sm, int *out, int *in) {
     cudaEventElapsedTime(&ms, e0, e1);
     if (ms < best) best = ms;
   }
-  const double instr = (double)grid * 4 * iters * 32.0;  // warp instructions
+  const double per_iter = (KIND == 9 || KIND == 11) ? 48.0 : 32.0;
+  const double instr = (double)grid * 4 * iters * per_iter;  // warp instructions
   // per SMSP: warp instructions per clock at 1.965 GHz
   const double ipc = instr / (148.0 * 4) / (best * 1e-3 * 1.965e9);
   printf("op %-44s %d CTAs/SM: %8.1f Glane-instr/s  IPC/SMSP@1965 = %.3f\n", name, ctas_per_sm,
@@ -249,6 +281,62 @@ __global__ void __launch_bounds__(128, MINB) loop16(unsigned *out, const unsigne
   out[(blockIdx.x * 128 + threadIdx.x) & 1023] = s;
 }
 
+// Variant: the cost table belongs to the COLUMN (two registers per DP column: gains of the column's
+// letter pair against the four row letters) and the selector to the ROW: PRMT(colA, colB, rsel[r]).
+// The two table operands are the same for all rows of a column (operand reuse cache), and a row
+// needs one register instead of two.
+template <int R, int ORDER>
+__device__ __forceinline__ void block16c(unsigned (&h)[R], unsigned &dg, const unsigned (&rsel)[R],
+                                         const unsigned (&up_in)[4], unsigned ywa, unsigned ywb, unsigned (&outv)[4],
+                                         unsigned one, unsigned cbase, unsigned cdelta) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const unsigned ta = cbase ^ (cdelta << ((ywa >> (8 * c)) & 24u));
+    const unsigned tb = cbase ^ (cdelta << ((ywb >> (8 * c)) & 24u));
+    unsigned diag = dg, up = up_in[c];
+    dg = up;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const unsigned left = h[r];
+      unsigned cost;
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(cost) : "r"(ta), "r"(tb), "r"(rsel[r]));
+      unsigned t;
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(diag), "r"(one), "r"(cost));
+      const unsigned v = ORDER ? __vimax3_u16x2(left, up, t) : __vimax3_u16x2(up, left, t);
+      diag = left;
+      up = v;
+      h[r] = v;
+    }
+    outv[c] = up;
+  }
+}
+
+template <int R, int ORDER, int MINB>
+__global__ void __launch_bounds__(128, MINB) loop16c(unsigned *out, const unsigned *yws, int n, unsigned one) {
+  unsigned h[R], rsel[R], dg = 0, outv[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    h[r] = 0;
+    rsel[r] = 0xC480u | (out[(r + threadIdx.x) & 1023] & 0x0303u);
+  }
+  const unsigned cbase = out[5] & 0x01010101u, cdelta = (out[6] & 3u) + 1u;
+  for (int q = 0; q < n; ++q) {
+    unsigned up_in[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) up_in[c] = __shfl_up_sync(0xffffffffu, outv[c], 1);
+    block16c<R, ORDER>(h, dg, rsel, up_in, yws[q & 1023], yws[(q + 32) & 1023], outv, one, cbase, cdelta);
+    if ((q & 255) == 255) {
+      const unsigned base = __shfl_sync(0xffffffffu, h[0], 0) & 0x7fff7fffu;
+#pragma unroll
+      for (int r = 0; r < R; ++r) h[r] = __vsub2(h[r], base);
+    }
+  }
+  unsigned s = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) s += h[r];
+  out[(blockIdx.x * 128 + threadIdx.x) & 1023] = s;
+}
+
 template <typename K>
 void time_loop(const char *name, K kernel, int R, int cells_per_reg, int blocks_per_sm, int regs, int maxb,
                void (*launch)(int, int, void *, void *, int), void *out, void *y) {
@@ -315,6 +403,10 @@ int main() {
     run_op<5>("IDP.4A distinct + VIMNMX (2 sources)", nb, out, in);
     run_op<6>("IMAD (2 reg sources) + VIMNMX3 distinct", nb, out, in);
     run_op<7>("VIMNMX3, one shared source", nb, out, in);
+    run_op<8>("VIMNMX3.U16x2 distinct", nb, out, in);
+    run_op<9>("PRMT + IMAD + VIMNMX3.U16x2", nb, out, in);
+    run_op<10>("PRMT + VIMNMX3.U16x2", nb, out, in);
+    run_op<11>("PRMT(2 shared) + IMAD + VIMNMX3.U16x2", nb, out, in);
   }
   cudaMemset(out, 1, 4096);
   RUN32(0, 32, 4, 4, "32-bit column-major");
@@ -333,6 +425,25 @@ int main() {
   RUN16(8, 1, 12, 12, "16x2 add on FMA pipe");
   RUN16(32, 1, 3, 3, "16x2 add on FMA pipe");
   RUN16(32, 1, 4, 4, "16x2 add on FMA pipe");
+#define RUN16C(R, ORDER, MINB, NB, NAME)                                                                \
+  {                                                                                                     \
+    auto k = loop16c<R, ORDER, MINB>;                                                                   \
+    int nb = 0;                                                                                         \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 128, 0);                                      \
+    cudaFuncAttributes at;                                                                              \
+    cudaFuncGetAttributes(&at, k);                                                                      \
+    time_loop(NAME, k, R, 2, NB, at.numRegs, nb,                                                        \
+              [](int g, int, void *o, void *y, int n) { loop16c<R, ORDER, MINB><<<g, 128>>>((unsigned *)o, (const unsigned *)y, n, 1u); }, \
+              out, y);                                                                                  \
+  }
+  RUN16C(16, 0, 4, 4, "16x2 column tables");
+  RUN16C(16, 1, 4, 4, "16x2 column tables, left first");
+  RUN16C(16, 1, 6, 6, "16x2 column tables, left first");
+  RUN16C(16, 1, 8, 8, "16x2 column tables, left first");
+  RUN16C(32, 0, 4, 4, "16x2 column tables");
+  RUN16C(32, 1, 4, 4, "16x2 column tables, left first");
+  RUN16C(32, 1, 5, 5, "16x2 column tables, left first");
+  RUN16C(8, 1, 8, 8, "16x2 column tables, left first");
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
