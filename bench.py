@@ -5,12 +5,20 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-A step = one full all-pairs job (getMinimumPenalties) over the named synthetic workload:
-every pair's DP fill + traceback + per-pair SHA-512 on the GPU(s), gather in the reference's
-task order, ordered hash chain on rank 0.  `value` = cells / step time with the sequences
-already resident in HBM and the batches planned; `e2e` = the same job through the public
-call with HOST buffers (H2D of the inputs, D2H of penalties + digests, chain) in the timed
-region.  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every field.
+A step = one full all-pairs job (getMinimumPenalties) over the named synthetic workload: every
+pair's DP fill + traceback + per-pair SHA-512 on the GPU(s), gather in the reference's task
+order, ordered hash chain on the host.
+  value      cells / step time with the sequences resident in HBM and the batches planned; one
+             process per GPU, barrier + max over ranks (at N > 1: NCCL all_gather per chunk).
+  e2e        the same job through the drop-in C ABI call `seqalk_all_pairs` with HOST buffers (H2D of
+             the inputs, D2H of penalties + digests, chain) in the timed region.  At N > 1 rank 0
+             makes that one call with seqalk_init(N): one host thread per GPU, results gathered by
+             peer stores over NVLink from the digest kernel (the fused path); the torchrun / NCCL
+             figure of the same job is kept as `e2e_nccl`.
+  parity     the GPU result on a bounded sample of the workload against the CPU arm (the
+             unmodified reference build, or the oracle port) in the same run, plus the committed
+             full-size oracle goldens; a mismatch makes the process exit non-zero.
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
 
@@ -27,8 +35,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "multiple-sequence-alignment-openmp-openmpi_b200"
-OPS_PER_CELL = 10  # algorithmic int32 lane-ops per DP cell
-EXECUTED_PER_CELL = 2.47  # lane-instructions the tile-mode fill executes per cell (ncu, profiles/)
+SURVEY_OPS_PER_CELL = 10  # the survey's model of int32 lane-ops per DP cell
 
 
 def parse_args():
@@ -40,6 +47,8 @@ def parse_args():
     ap.add_argument("--workload", default="cfg4")
     ap.add_argument("--nchunks", type=int, default=0, help="gather/fold chunks (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 / cfg3 / cfg5 sub-objects (N = 1)")
+    ap.add_argument("--no-inprocess", action="store_true", help="N > 1: skip the in-process fused run on rank 0")
     return ap.parse_args()
 
 
@@ -94,20 +103,22 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------------------------- CPU arm
+
 def cpu_sample(genes, n_seq=16):
-    """Bounded CPU sample of the workload: its first n_seq sequences, all pairs among them."""
+    """Bounded CPU sample of a workload: its first n_seq sequences (all pairs among them); the single
+    200 000 x 200 000 pair of cfg5 is cut to its 50 000 x 50 000 prefix (the reference needs 4 mn bytes)."""
+    if len(genes) == 2:
+        return [g[:50000] for g in genes]
     return genes[:n_seq]
 
 
-def run_cpu_baseline(workloads, pxy, pgap, genes, workload_name):
+def run_cpu_baseline(workloads, pxy, pgap, genes, workload_name, n_seq=16):
     """The reference's own CPU implementation (oracle/_ref/ref_par = unmodified
     submit/xuliny-seqalkway.cpp + single-rank mpi.h shim) if it was built, else the oracle port."""
     from oracle import binding as oracle  # checker / baseline only
 
-    n_seq = 2 if len(genes) == 2 else 16
     sample = cpu_sample(genes, n_seq)
-    if len(genes) == 2:  # cfg5: the reference cannot allocate 200k x 200k ints; 50 000^2 prefix
-        sample = [g[:50000] for g in genes]
     cells = workloads.total_cells(sample)
     doc = workloads.format_input(pxy, pgap, sample)
     ncpu = os.cpu_count() or 1
@@ -115,13 +126,73 @@ def run_cpu_baseline(workloads, pxy, pgap, genes, workload_name):
     if os.path.exists(oracle.REF_PAR):
         t_us, digest, pen = oracle.run_reference(oracle.REF_PAR, doc)
         # the submission hard-codes 15 compute + 2 control threads on rank 0 (:94,238,272,425)
+        note = "17 threads hard-coded by the reference (15 compute + 2 control)"
+        if ncpu < 17:
+            note += f"; oversubscribed on this host's {ncpu} CPUs"
         return {"value": cells / (t_us * 1e-6) / 1e9, "unit": "GCUPS", "cores": min(ncpu, 17), "kind": "reference",
-                "threads": 17, "host_cpus": ncpu, "sample": desc, "seconds": t_us * 1e-6, "digest": digest}
+                "threads": 17, "host_cpus": ncpu, "threads_note": note, "sample": desc, "seconds": t_us * 1e-6,
+                "digest": digest, "penalties": [int(v) for v in pen]}
     t0 = time.perf_counter()
     digest, pen, _ = oracle.all_pairs(sample, pxy, pgap, nthreads=0)
     dt = time.perf_counter() - t0
     return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": ncpu, "kind": "port", "host_cpus": ncpu,
-            "sample": desc, "seconds": dt, "digest": digest}
+            "sample": desc, "seconds": dt, "digest": digest, "penalties": [int(v) for v in pen]}
+
+
+def parity_check(pkg, workloads, pxy, pgap, genes, workload_name, base, n_seq):
+    """GPU vs CPU on the sample the CPU arm ran (`base`, or the oracle port when there is none).
+    The unmodified reference's threaded build gave a wrong digest once in ~10 runs on a 32-vCPU
+    box in round 1 (nested OpenMP in the reference, not the product): on a mismatch the sample is
+    re-run with the sequential reference build / the oracle before the verdict."""
+    from oracle import binding as oracle  # checker only
+
+    sample = cpu_sample(genes, n_seq)
+    gd, gp = pkg.get_minimum_penalties(sample, pxy, pgap)
+    out = {"sample": f"{workload_name}: first {len(sample)} sequences, {len(sample) * (len(sample) - 1) // 2} pairs",
+           "sample_digest_gpu": gd}
+    if base is not None and base.get("digest"):
+        cd, cp, kind = base["digest"], base.get("penalties"), base["kind"]
+    else:
+        cd, cp_arr, _ = oracle.all_pairs(sample, pxy, pgap, nthreads=0)
+        cp, kind = [int(v) for v in cp_arr], "port"
+    out["sample_digest_cpu"], out["cpu_kind"] = cd, kind
+    match = gd == cd and (cp is None or [int(v) for v in gp] == list(cp))
+    if not match:
+        od, op, _ = oracle.all_pairs(sample, pxy, pgap, nthreads=0)
+        out["sample_digest_oracle"] = od
+        if os.path.exists(oracle.REF_SEQ) and workloads.total_cells(sample) < 3e9:
+            _, sd, _ = oracle.run_reference(oracle.REF_SEQ, workloads.format_input(pxy, pgap, sample))
+            out["sample_digest_ref_seq"] = sd
+        if od == gd and [int(v) for v in op] == [int(v) for v in gp]:
+            out["cpu_arm_irreproducible"] = True  # the threaded reference run disagreed with oracle == GPU
+            match = True
+    out["match"] = bool(match)
+    return out
+
+
+def golden_check(workload_name, digest, penalties):
+    """The committed oracle goldens of the BASELINE configs (tests/golden): full digest where one
+    exists (cfg2, cfg3, cfg5), the 2 027 stratified sample penalties for cfg4."""
+    gdir = os.path.join(ROOT, "tests", "golden")
+    try:
+        if workload_name == "cfg2":
+            e = json.load(open(os.path.join(gdir, "expected.json")))["big13"]
+            return {"kind": "reference captured output (testing15/sample.txt)",
+                    "match": digest == e["digest"] and [int(v) for v in penalties] == e["penalties"]}
+        full = json.load(open(os.path.join(gdir, "fullsize.json")))
+        if workload_name == "cfg3" and "cfg3" in full:
+            g = full["cfg3"]
+            return {"kind": "oracle, full job", "match": digest == g["digest"] and [int(v) for v in penalties] == g["penalties"]}
+        if workload_name == "cfg5":
+            g = full["cfg5"]
+            return {"kind": "oracle, full pair", "match": digest == g["digest"] and int(penalties[0]) == g["penalty"]}
+        if workload_name == "cfg4":
+            g = full["cfg4"]
+            ok = all(int(penalties[t]) == p for t, p in zip(g["task_ids"], g["penalties"]))
+            return {"kind": f"oracle, penalties of {len(g['task_ids'])} stratified tasks", "match": bool(ok)}
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
 
 
 def main_reference(args, rank):
@@ -140,6 +211,7 @@ def main_reference(args, rank):
             vals.append(base["value"])
     v = statistics.mean(vals)
     base["value"] = v
+    base.pop("penalties", None)
     line = {"impl": "reference", "metric": "all-pairs GCUPS", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
@@ -149,6 +221,31 @@ def main_reference(args, rank):
             "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+
+def fill_kernel_model(stats, peaks):
+    """What bounds the dominant kernel, per fill variant (SASS-verified instruction mix per cell):
+      packed 16x2 fill (fill16.cu):  per TWO cells PRMT + VIMNMX3.U16x2 on the ALU pipe and one IMAD
+                                     on the FMA pipe -> 1 ALU instruction per cell: ALU-pipe bound;
+      32-bit score-only fill:        per cell IDP.4A (FMA pipe) + VIMNMX3 (ALU pipe): issue-slot
+                                     bound (2 instructions per cell at the measured dual-issue rate);
+      directions-mode fill:          per cell VIMNMX3 + 2 SHF on the ALU pipe (3 per cell)."""
+    if stats.get("fill_packed16"):
+        return {"bound": "alu_pipe", "ops_per_cell": 1.0, "peak": peaks["vimnmx3.u16x2"],
+                "peak_source": "measured live: VIMNMX3.U16x2 issue rate with three different register operands "
+                               "(seqalk_measure_int_peaks[12]) = the ALU pipe, 64 lanes/clk/SM",
+                "kernel": "fill16_kernel<16,6> (two DP cells per register)",
+                "sass": "per 2 cells: PRMT (ALU) + IMAD (FMA) + VIMNMX3.U16x2 (ALU); profiles/r02_fill16_sass.txt"}
+    if stats.get("tile_mode"):
+        return {"bound": "issue (ALU+FMA dual)", "ops_per_cell": 2.0, "peak": peaks["idp4a+vimnmx3"],
+                "peak_source": "measured live: IDP.4A + VIMNMX3 alternating (seqalk_measure_int_peaks[9])",
+                "kernel": "fill_kernel<32,TAB,IDP.4A,score-only>",
+                "sass": "per cell: IDP.4A (FMA) + VIMNMX3 (ALU); profiles/r01_fill_tiles_cfg4_final_ncu_summary.txt"}
+    return {"bound": "alu_pipe", "ops_per_cell": 3.0, "peak": peaks["lop3"],
+            "peak_source": "measured live: LOP3 issue rate (ALU pipe)", "kernel": "fill_kernel<16,..,directions>",
+            "sass": "per cell: VIMNMX3 + 2 SHF.L.W (ALU), IDP.4A + 2 IMAD (FMA)"}
 
 
 def main():
@@ -175,14 +272,6 @@ def main():
     if world != args.gpus and rank == 0:
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
-    pxy, pgap, genes = workloads.make(args.workload)
-    lens = [len(g) for g in genes]
-    cells = workloads.total_cells(genes)
-    T = len(genes) * (len(genes) - 1) // 2
-    # chunks of task ids: rank 0 folds the hash chain of chunk c while the GPUs work on chunk c+1
-    # (chunks of >= 32k tasks: smaller ones only add kernel tails)
-    nchunks = args.nchunks or max(1, min(8, T // 32768))
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -205,138 +294,256 @@ def main():
 
     peaks = pkg.measure_int_peaks(local_rank) if rank == 0 else None
 
-    # ---- value: inputs resident in HBM, batches planned
-    plan = dmod.ShardPlan(lens, world, nchunks)
-    shard = dmod.GpuShard(genes, pxy, pgap, plan, rank, local_rank)
-    result = None
+    def measure(workload_name, steps, warmup, sample_clocks):
+        """One workload: resident `value` loop + e2e loop.  Returns a dict (rank 0) or None."""
+        pxy, pgap, genes = workloads.make(workload_name)
+        lens = [len(g) for g in genes]
+        cells = workloads.total_cells(genes)
+        T = len(genes) * (len(genes) - 1) // 2
+        # chunks of task ids: rank 0 folds the hash chain of chunk c while the GPUs work on chunk c+1
+        # (chunks of >= 32k tasks: smaller ones only add kernel tails)
+        nchunks = args.nchunks or max(1, min(8, T // 32768))
+        plan = dmod.ShardPlan(lens, world, nchunks)
+        shard = dmod.GpuShard(genes, pxy, pgap, plan, rank, local_rank)
+        result = None
 
-    def step_resident():
-        nonlocal result
-        shard.start()
-        result = dmod.run_sharded(plan, rank, shard.run_chunk)
-        shard.finish()
+        def step_resident():
+            nonlocal result
+            shard.start()
+            result = dmod.run_sharded(plan, rank, shard.run_chunk)
+            shard.finish()
 
-    for _ in range(args.warmup):
+        for _ in range(warmup):
+            barrier()
+            step_resident()
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        step_s, fill_ms, tb_ms, dg_ms, launches, dir_bytes, my_cells = [], 0.0, 0.0, 0.0, 0, 0, 0
+        stats0 = {}
+        for _ in range(steps):
+            barrier()
+            t0 = time.perf_counter()
+            step_resident()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            step_s.append(max_over_ranks(dt))
+            st = shard.stats()
+            fill_ms += sum(s.fill_ms for s in st)
+            tb_ms += sum(s.traceback_ms for s in st)
+            dg_ms += sum(s.digest_ms for s in st)
+            launches += sum(s.fill_launches + s.traceback_launches + s.digest_launches for s in st)
+            dir_bytes = sum(s.dir_bytes for s in st)
+            my_cells = sum(s.cells for s in st)
+            if st:
+                stats0 = dict(st[0])
         barrier()
-        step_resident()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    step_s, fill_ms, tb_ms, dg_ms, launches, dir_bytes = [], 0.0, 0.0, 0.0, 0, 0
-    for _ in range(args.steps):
+        clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+        digest_resident, pen_resident = (result if rank == 0 else (None, None))
+        shard.close()
+        del shard
+
+        # per-rank device-side kernel time (CUDA events on the launching streams)
+        fill_ms_max = max_over_ranks(fill_ms / steps)
+        total_launches = int(sum_over_ranks(float(launches)))
+        my_rate = my_cells / (fill_ms / steps * 1e-3) if fill_ms > 0 else 0.0  # cells/s inside the fill kernels
+        fill_cups = sum_over_ranks(my_rate) / world
+        dir_rate = sum_over_ranks(dir_bytes / (fill_ms / steps * 1e-3) if fill_ms > 0 else 0.0) / world
+
+        # ---- e2e: host buffers in, host results out.  N = 1: the C ABI call.  N > 1: the torchrun /
+        # NCCL form here (kept as e2e_nccl); the C ABI call with seqalk_init(N) follows after teardown.
+        e2e_s, digest_e2e, pen_e2e = [], None, None
+        for _ in range(steps):
+            barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                digest_e2e, pen_e2e = pkg.get_minimum_penalties(genes, pxy, pgap)
+            else:
+                r = dmod.all_pairs_distributed(genes, pxy, pgap, nchunks=nchunks, device=local_rank)
+                if rank == 0:
+                    digest_e2e, pen_e2e = r
+            torch.cuda.synchronize()
+            e2e_s.append(max_over_ranks(time.perf_counter() - t0))
         barrier()
-        t0 = time.perf_counter()
-        step_resident()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        step_s.append(max_over_ranks(dt))
-        st = shard.stats()
-        fill_ms += sum(s.fill_ms for s in st)
-        tb_ms += sum(s.traceback_ms for s in st)
-        dg_ms += sum(s.digest_ms for s in st)
-        launches += sum(s.fill_launches + s.traceback_launches + s.digest_launches for s in st)
-        dir_bytes = sum(s.dir_bytes for s in st)
-        my_cells = sum(s.cells for s in st)
-        tile_mode = max((s.tile_mode for s in st), default=0)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    digest_resident = result[0] if rank == 0 else None
-    shard.close()
-    del shard
+        if rank != 0:
+            return None
+        ms = statistics.mean(step_s) * 1e3
+        e2e_ms = statistics.mean(e2e_s) * 1e3
+        return {"name": workload_name, "pxy": pxy, "pgap": pgap, "genes": genes, "lens": lens, "cells": cells, "T": T,
+                "nchunks": nchunks, "ms": ms, "e2e_ms": e2e_ms, "clocks": clocks, "stats": stats0,
+                "fill_ms": fill_ms / steps, "tb_ms": tb_ms / steps, "dg_ms": dg_ms / steps,
+                "fill_ms_max": fill_ms_max, "launches": total_launches, "fill_cups": fill_cups, "dir_rate": dir_rate,
+                "digest": digest_resident, "penalties": pen_resident, "digest_e2e": digest_e2e,
+                "penalties_e2e": pen_e2e, "profile": pkg.last_profile() if world == 1 else None}
 
-    # per-rank device-side kernel time (CUDA events on the launching streams), max over ranks
-    fill_ms_max = max_over_ranks(fill_ms / args.steps)
-    total_launches = int(sum_over_ranks(float(launches)))
-    # the slowest rank bounds the step: its fill rate is the dominant-kernel figure
-    my_rate = (my_cells * OPS_PER_CELL) / (fill_ms / args.steps * 1e-3) if fill_ms > 0 else 0.0
-    agg_ops_rate = sum_over_ranks(my_rate)
-    agg_dir_rate = sum_over_ranks(dir_bytes / (fill_ms / args.steps * 1e-3) if fill_ms > 0 else 0.0)
+    M = measure(args.workload, args.steps, args.warmup, True)
 
-    # ---- e2e: host buffers in, host results out, through the public call
-    e2e_s = []
-    h2d = sum(lens) if world == 1 else sum(lens)  # every rank uploads the (replicated) inputs
-    d2h = T * 68
-    digest_e2e = None
-    for _ in range(args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            digest_e2e, pen_e2e = pkg.get_minimum_penalties(genes, pxy, pgap)
-        else:
-            r = dmod.all_pairs_distributed(genes, pxy, pgap, nchunks=nchunks, device=local_rank)
-            if rank == 0:
-                digest_e2e, pen_e2e = r
-        torch.cuda.synchronize()
-        e2e_s.append(max_over_ranks(time.perf_counter() - t0))
-    barrier()
+    # ---- secondary BASELINE configs (N = 1): one line per config inside the same JSON object
+    secondary = {}
+    if world == 1 and not args.no_secondary:
+        for name in ("cfg2", "cfg3", "cfg5"):
+            if name == args.workload:
+                continue
+            try:
+                m = measure(name, 2, 1, False)
+                g = golden_check(name, m["digest_e2e"], m["penalties_e2e"])
+                secondary[name] = {
+                    "workload": workloads.CONFIGS[name][0], "cells": m["cells"], "pairs": m["T"],
+                    "value": m["cells"] / (m["ms"] * 1e-3) / 1e9, "ms_per_step": m["ms"],
+                    "e2e": {"value": m["cells"] / (m["e2e_ms"] * 1e-3) / 1e9, "ms_per_step": m["e2e_ms"]},
+                    "unit": "GCUPS", "steps": 2, "warmup": 1,
+                    "kernel_ms_per_step": {"fill": m["fill_ms"], "traceback": m["tb_ms"], "digest": m["dg_ms"]},
+                    "fill_gcups": m["fill_cups"] / 1e9, "fill_packed16": int(m["stats"].get("fill_packed16", 0)),
+                    "digest": m["digest"], "digest_e2e_matches": m["digest"] == m["digest_e2e"], "golden": g}
+            except Exception as e:  # a secondary config must never sink the headline
+                secondary[name] = {"error": repr(e)}
 
+    line = None
+    exit_code = 0
     if rank == 0:
         # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this
         # workload (profiles/traffic.json), per launch; null when no capture exists for it
         ncu_traffic = {}
         try:
             allt = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            ncu_traffic = allt.get(f"{args.workload}:{'tiles' if tile_mode else 'dirs'}", {})
+            variant = "tiles16" if M["stats"].get("fill_packed16") else ("tiles" if M["stats"].get("tile_mode") else "dirs")
+            ncu_traffic = allt.get(f"{args.workload}:{variant}", {})
         except (OSError, ValueError):
             pass
-        ms = statistics.mean(step_s) * 1e3
-        value = cells / (ms * 1e-3) / 1e9
-        e2e_ms = statistics.mean(e2e_s) * 1e3
-        peak = peaks["lop3"]
+        cells, ms, e2e_ms = M["cells"], M["ms"], M["e2e_ms"]
+        clocks = M["clocks"]
         sm_mhz = clocks.get("sm_mhz") or 0
+        model = fill_kernel_model(M["stats"], peaks)
+        fill_gcups = M["fill_cups"] / 1e9
+        achieved = fill_gcups * model["ops_per_cell"]  # G lane-instructions/s on the bounding resource
+        hbm_peak = 6650.0
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        tile_mode = int(M["stats"].get("tile_mode", 0))
         line = {
-            "metric": "all-pairs GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workloads.CONFIGS[args.workload][0], "name": args.workload, "pxy": pxy,
-                       "pgap": pgap, "k": len(genes), "pairs": T, "cells": cells, "sharding": f"lpt-cells x{world}",
-                       "gather_chunks": nchunks,
+            "metric": "all-pairs GCUPS", "value": cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workloads.CONFIGS[args.workload][0], "name": args.workload, "pxy": M["pxy"],
+                       "pgap": M["pgap"], "k": len(M["genes"]), "pairs": M["T"], "cells": cells,
+                       "sharding": f"lpt-cells x{world}", "gather_chunks": M["nchunks"],
                        "traceback": "tiles (score-only fill + per-tile recompute)" if tile_mode else "dirs (2-bit directions in HBM)",
+                       "fill": "16x2-packed (fill16.cu)" if M["stats"].get("fill_packed16") else "32-bit (fill.cu)",
                        "l2": "working set (checkpoints / packed directions: tens of GB per batch, every step a new pass over them) far exceeds the 126 MB L2; no flush needed"},
             "clocks": clocks,
             "e2e": {"value": cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h},
-            "gpu_launches": total_launches,
+                    "h2d_bytes_per_step": sum(M["lens"]) * world, "d2h_bytes_per_step": M["T"] * 68,
+                    "path": "seqalk_all_pairs (C ABI, host buffers)" if world == 1 else "torchrun + NCCL all_gather (see e2e_nccl; replaced below by the in-process call)"},
+            "gpu_launches": M["launches"],
             "roofline": {
-                "bound": "int_alu", "achieved": agg_ops_rate / world / 1e9, "peak": peak / 1e9, "unit": "Gop/s",
-                "frac": (agg_ops_rate / world) / peak if peak else None,
+                "bound": model["bound"], "achieved": achieved, "peak": model["peak"] / 1e9, "unit": "G lane-instr/s",
+                "frac": achieved / (model["peak"] / 1e9) if model["peak"] else None,
                 "traffic": ncu_traffic.get("dram_bytes_per_launch"), "traffic_source": ncu_traffic.get("source"),
-                "per": "GPU (mean over ranks)", "ops_per_cell": OPS_PER_CELL,
-                "peak_source": "measured live: dependent-free LOP3 issue rate (seqalk_measure_int_peaks), ALU pipe",
+                "per": "GPU (mean over ranks)", "ops_per_cell": model["ops_per_cell"], "kernel": model["kernel"],
+                "sass": model["sass"], "peak_source": model["peak_source"],
+                "fill_gcups_per_gpu": fill_gcups, "fill_ms_per_step_max_rank": M["fill_ms_max"],
                 "peak_nominal_at_sm_mhz": 148 * 64 * sm_mhz * 1e6 / 1e9 if sm_mhz else None,
-                "issue_rates_gops": {k: v / 1e9 for k, v in peaks.items()},
-                "fill_gcups_per_gpu": agg_ops_rate / world / OPS_PER_CELL / 1e9,
-                # the same kernel against the machine's real issue ceiling: executed warp
-                # instructions per cell from the committed ncu capture (tile-mode fill: 2.67
-                # lane-instructions per cell incl. loop bookkeeping) vs the measured ALU+FMA
-                # dual-issue rate (LOP3+IMAD microbenchmark)
-                "issue": {"lane_instr_per_cell": EXECUTED_PER_CELL,
-                          "achieved": agg_ops_rate / world / OPS_PER_CELL * EXECUTED_PER_CELL / 1e9,
-                          "peak": peaks["lop3+imad"] / 1e9, "unit": "Ginstr/s",
-                          "frac": (agg_ops_rate / world / OPS_PER_CELL * EXECUTED_PER_CELL) / peaks["lop3+imad"]
-                          if tile_mode else None,
-                          "source": "profiles/r01_fill_tiles_cfg4_final_ncu_summary.txt"},
-                "fill_ms_per_step_max_rank": fill_ms_max,
-                "hbm": {"bound": "hbm", "achieved": agg_dir_rate / world / 1e9, "unit": "GB/s",
-                        "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-                        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
-                        "note": "algorithmic bytes written by the fill: 0.25 B/cell of packed directions (dirs mode) "
-                                "or the kept rows + column checkpoints (tiles mode)"},
+                "issue_rates_gops": {k: v / 1e9 for k, v in peaks.items() if k != "reserved"},
+                # the survey's own model (10 int32 lane-ops per cell against the LOP3 rate) for the
+                # record: the kernels need far fewer instructions per cell, so this is not a fraction
+                "survey_model": {"ops_per_cell": SURVEY_OPS_PER_CELL, "achieved": fill_gcups * SURVEY_OPS_PER_CELL,
+                                 "peak": peaks["lop3"] / 1e9, "ratio": fill_gcups * SURVEY_OPS_PER_CELL / (peaks["lop3"] / 1e9)},
+                # executed lane-instructions per cell incl. bookkeeping, ramps and row padding, from the
+                # committed ncu capture of this build's fill kernel (not measured live)
+                "executed": ncu_traffic.get("executed"),
+                "hbm": {"bound": "hbm", "achieved": M["dir_rate"] / 1e9, "unit": "GB/s", "peak": hbm_peak,
+                        "frac": M["dir_rate"] / 1e9 / hbm_peak,
+                        "note": "algorithmic bytes written by the fill: kept rows + column checkpoints (tiles mode) "
+                                "or 0.25 B/cell of packed directions (dirs mode)"},
             },
-            "kernel_ms_per_step": {"fill": fill_ms / args.steps, "traceback": tb_ms / args.steps,
-                                   "digest": dg_ms / args.steps, "note": "rank 0, CUDA events on the launching streams"},
-            "digest": digest_resident, "digest_e2e_matches": digest_resident == digest_e2e,
+            "kernel_ms_per_step": {"fill": M["fill_ms"], "traceback": M["tb_ms"], "digest": M["dg_ms"],
+                                   "note": "rank 0, CUDA events on the launching streams"},
+            "self_checked": int(M["stats"].get("self_checked", 0)),
+            "digest": M["digest"], "digest_e2e_matches": M["digest"] == M["digest_e2e"],
         }
-        line["roofline"]["hbm"]["frac"] = line["roofline"]["hbm"]["achieved"] / line["roofline"]["hbm"]["peak"]
+        if M["profile"]:
+            line["e2e"]["phases_ms"] = {k: M["profile"][k] for k in ("setup_ms", "gpu_span_ms", "fold_exposed_ms")}
+        if secondary:
+            line["configs"] = secondary
+
+    # ---- N > 1: the fused in-process path through the C ABI (rank 0 alone drives all N GPUs)
+    if world > 1:
+        # every rank releases its GPU memory before rank 0 takes over the whole box
+        pkg.shutdown()
+        torch.cuda.empty_cache()
+        barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return 0
+        if not args.no_inprocess:
+            try:
+                t_wait = time.time()
+                while time.time() - t_wait < 60:  # the other ranks' contexts are gone once their processes exit
+                    free = [torch.cuda.mem_get_info(d) for d in range(world)]
+                    if all(f / t > 0.9 for f, t in free):
+                        break
+                    time.sleep(0.5)
+                genes, pxy, pgap = M["genes"], M["pxy"], M["pgap"]
+                pkg.init(world)
+                pkg.get_minimum_penalties(genes, pxy, pgap)  # warm-up: buffers, peer mappings
+                times, dig_in, pen_in = [], None, None
+                for _ in range(args.steps):
+                    t0 = time.perf_counter()
+                    dig_in, pen_in = pkg.get_minimum_penalties(genes, pxy, pgap)
+                    times.append(time.perf_counter() - t0)
+                prof = pkg.last_profile()
+                in_ms = statistics.mean(times) * 1e3
+                line["e2e_nccl"] = dict(line["e2e"], path="one process per GPU (torchrun), NCCL all_gather per chunk, scatter + fold on rank 0")
+                line["e2e"] = {"value": M["cells"] / (in_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": in_ms,
+                               "h2d_bytes_per_step": sum(M["lens"]) * world, "d2h_bytes_per_step": M["T"] * 68,
+                               "path": f"seqalk_init({world}) + seqalk_all_pairs (C ABI, host buffers): one host thread per GPU, "
+                                       "results gathered by peer stores over NVLink from the digest kernel",
+                               "digest_matches": dig_in == M["digest"], "gpus_used": pkg.device_count()}
+                kern_mean = prof["kernel_ms_mean_gpu"]
+                line["scaling_loss"] = {
+                    "call_ms": prof["call_ms"], "setup_ms": prof["setup_ms"], "gpu_span_ms": prof["gpu_span_ms"],
+                    "kernel_ms_mean_gpu": kern_mean, "kernel_ms_max_gpu": prof["kernel_ms_max_gpu"],
+                    "kernel_tail_ms": prof["gpu_span_ms"] - kern_mean,
+                    "fold_exposed_ms": prof["fold_exposed_ms"], "gather_ms": prof["gather_d2h_ms"],
+                    "chunks": int(prof["chunks"]),
+                    "note": "in-process call on rank 0: kernel_tail = time inside the GPU span not covered by the mean "
+                            "GPU's kernels (launch gaps, per-chunk tails, imbalance); fold_exposed = chain fold left after the last chunk"}
+                if dig_in != M["digest"]:
+                    exit_code = 3
+                M["penalties_e2e"], M["digest_e2e"] = pen_in, dig_in
+            except Exception as e:
+                line["e2e_inprocess_error"] = repr(e)
+
+    if rank == 0:
+        # ---- CPU arm + parity gate
+        base = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = run_cpu_baseline(workloads, pxy, pgap, genes, args.workload)
+                base = run_cpu_baseline(workloads, M["pxy"], M["pgap"], M["genes"], args.workload)
             except Exception as e:  # the baseline must never sink the GPU number
+                base = None
                 line["cpu_baseline"] = {"value": None, "error": repr(e)}
+        try:
+            if world > 1:
+                pkg.init(1)
+            par = parity_check(pkg, workloads, M["pxy"], M["pgap"], M["genes"], args.workload, base,
+                               16 if world == 1 else 8)
+            g = golden_check(args.workload, M["digest_e2e"], M["penalties_e2e"])
+            if g is not None:
+                par["golden"] = g
+            par["match"] = bool(par["match"] and (g is None or g["match"]) and line["digest_e2e_matches"])
+            line["parity"] = par
+            if not par["match"]:
+                exit_code = 3
+        except Exception as e:
+            line["parity"] = {"match": False, "error": repr(e)}
+            exit_code = 3
+        if base is not None:
+            base.pop("penalties", None)
+            line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return exit_code
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main() or 0)

@@ -69,6 +69,15 @@ int seqalk_all_pairs_scores(const char *const *seqs, const int32_t *lens, int32_
 int seqalk_pair_score(const char *x, int32_t m, const char *y, int32_t n, int32_t pxy, int32_t pgap,
                       int32_t *penalty_out);
 
+/* Phase times (milliseconds) of the last seqalk_all_pairs call of this process, for tracing the
+ * scaling losses: [0] whole call, [1] set-up (pack, partition, H2D, plan), [2] from the first
+ * launch until every GPU finished its last chunk, [3] hash-chain fold (and last D2H) left exposed
+ * after that, [4] D2H copies of the gathered results, [5] kernel time (fill + traceback + digest,
+ * CUDA events) of the busiest GPU, [6] mean kernel time over the GPUs, [7] GPUs, [8] chunks (N > 1)
+ * or batches (N = 1), [9..11] fill / traceback / digest kernel time summed over the GPUs. */
+#define SEQALK_PROFILE_LEN 12
+int seqalk_profile(double *out, int32_t n);
+
 /* ---- sharded execution: one process per GPU ------------------------------------------- */
 
 /* T = k(k-1)/2 */
@@ -156,9 +165,12 @@ int seqalk_sha512_hex(const void *data, size_t len, char out[129]);
  * alternating (dual pipe), [4] VIADDMNMX (fused add+min), [5] SHF (funnel shift),
  * [6] LOP3+VIMNMX3 alternating, [7] the directions-mode fill mix (1 VIMNMX3 : 1 SHF : 2 IMAD),
  * [8] IDP.4A (byte dot product + add), [9] IDP.4A+VIMNMX3 alternating, [10] IDP.4A+IMAD
- * alternating, [11] PRMT.
+ * alternating, [11] PRMT, [12] VIMNMX3.U16x2 (two 16-bit max3 per lane; counted as one lane-op),
+ * [13] the packed fill's mix PRMT + IMAD + VIMNMX3.U16x2 on different registers, [14] IDP.4A +
+ * VIMNMX3 with three different register operands per instruction (register-file bandwidth bound,
+ * unlike [9] whose operands sit in the reuse cache), [15] reserved.
  * rates_out[0] is the integer-ALU roofline denominator of SURVEY.md section 8d. */
-int seqalk_measure_int_peaks(int32_t device, double rates_out[12]);
+int seqalk_measure_int_peaks(int32_t device, double rates_out[16]);
 
 #ifdef __cplusplus
 }

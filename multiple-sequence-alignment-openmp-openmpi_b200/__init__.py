@@ -27,7 +27,7 @@ import numpy as np
 
 __all__ = [
     "SeqalkError", "lib", "library_path", "getMinimumPenalties", "getMinimumPenalty", "do_MPI_task",
-    "get_minimum_penalties", "get_minimum_penalty", "all_pairs_scores", "pair_score", "Job", "JobStats", "partition", "partition_all", "partition_chunks", "chunk_bounds", "task_ij",
+    "get_minimum_penalties", "get_minimum_penalty", "all_pairs_scores", "pair_score", "last_profile", "Job", "JobStats", "partition", "partition_all", "partition_chunks", "chunk_bounds", "task_ij",
     "num_tasks", "fold_chain", "sha512_hex", "init", "shutdown", "device_count", "version",
 ]
 
@@ -71,6 +71,7 @@ C_ABI = [
     ("seqalk_pair", _c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _I32P, _I32P, _I32P]),
     ("seqalk_all_pairs_scores", _c.c_int, [_c.POINTER(_c.c_void_p), _I32P, _c.c_int32, _c.c_int32, _c.c_int32, _I32P]),
     ("seqalk_pair_score", _c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32, _I32P]),
+    ("seqalk_profile", _c.c_int, [_c.POINTER(_c.c_double), _c.c_int32]),
     ("seqalk_num_tasks", _c.c_int64, [_c.c_int32]),
     ("seqalk_task_ij", _c.c_int, [_c.c_int64, _I32P, _I32P]),
     ("seqalk_partition", _c.c_int, [_I32P, _c.c_int32, _c.c_int64, _c.c_int64, _c.c_int32, _c.c_int32, _I64P, _I64P]),
@@ -206,6 +207,17 @@ def pair_score(x, y, pxy: int, pgap: int) -> int:
     _check(lib().seqalk_pair_score(ctypes.cast(xbuf, ctypes.c_void_p), len(xb), ctypes.cast(ybuf, ctypes.c_void_p),
                                    len(yb), int(pxy), int(pgap), ctypes.byref(pen)))
     return int(pen.value)
+
+
+PROFILE_NAMES = ["call_ms", "setup_ms", "gpu_span_ms", "fold_exposed_ms", "gather_d2h_ms", "kernel_ms_max_gpu",
+                 "kernel_ms_mean_gpu", "gpus", "chunks", "fill_ms_sum", "traceback_ms_sum", "digest_ms_sum"]
+
+
+def last_profile() -> dict:
+    """Phase times of the last get_minimum_penalties call of this process (``seqalk_profile``)."""
+    out = (ctypes.c_double * len(PROFILE_NAMES))()
+    _check(lib().seqalk_profile(out, len(PROFILE_NAMES)))
+    return dict(zip(PROFILE_NAMES, [float(v) for v in out]))
 
 
 def getMinimumPenalties(genes: Sequence, k: int, pxy: int, pgap: int, penalties) -> str:
@@ -422,12 +434,13 @@ def fold_chain(pair_digests: np.ndarray, state: str = "") -> str:
 
 
 INT_PEAK_NAMES = ["lop3", "vimnmx3", "imad", "lop3+imad", "viaddmnmx", "shf", "lop3+vimnmx3", "fill_mix",
-                  "idp4a", "idp4a+vimnmx3", "idp4a+imad", "prmt"]
+                  "idp4a", "idp4a+vimnmx3", "idp4a+imad", "prmt", "vimnmx3.u16x2", "prmt+imad+vimnmx3.u16x2",
+                  "idp4a+vimnmx3 distinct operands", "reserved"]
 
 
 def measure_int_peaks(device: int = 0) -> dict:
     """Issue-rate microbenchmarks (lane-ops/s) — the integer roofline denominators."""
-    r = (ctypes.c_double * 12)()
+    r = (ctypes.c_double * 16)()
     if lib().seqalk_measure_int_peaks(int(device), r) != 0:
         raise SeqalkError("seqalk_measure_int_peaks failed (no usable GPU?)")
     return dict(zip(INT_PEAK_NAMES, [float(v) for v in r]))

@@ -66,6 +66,8 @@ struct Runtime {
   // freeing peer-mapped memory inside the call cost up to 0.6 s on some boxes)
   void *pen0 = nullptr, *dig0 = nullptr;
   size_t res_cap = 0;  // tasks
+  // phase times of the last seqalk_all_pairs call (seqalk_profile)
+  double prof[SEQALK_PROFILE_LEN] = {0};
   void reserve_results(size_t tasks) {
     if (tasks <= res_cap) return;
     release_results();
@@ -215,6 +217,10 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
   std::vector<std::vector<std::vector<int64_t>>> per;
   partition_all_chunks(pack.len.data(), k, N, bounds, per);
   mark("partitioned");
+  auto ms_since = [&](std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+  };
+  for (double &v : r.prof) v = 0;
   r.reserve_results((size_t)T);
   int32_t *const pen0 = static_cast<int32_t *>(r.pen0);
   uint8_t *const dig0 = static_cast<uint8_t *>(r.dig0);
@@ -249,6 +255,8 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
       if (!errs[d].empty()) throw std::runtime_error("GPU " + std::to_string(d) + ": " + errs[d]);
   }
   mark("loaded and planned");
+  r.prof[1] = ms_since(t0);
+  const auto t_start = std::chrono::steady_clock::now();
   for (int d = 0; d < N; ++d) {
     try {
       r.workers[d]->start_async(pen0, dig0);
@@ -273,11 +281,14 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
         r.workers[d]->wait_chunk((size_t)c, nullptr);
         mark("chunk done on GPU", d);
       }
+      if (c == nchunks - 1) r.prof[2] = ms_since(t_start);  // every GPU has finished its last chunk
       const size_t lo = (size_t)bounds[c], n = (size_t)(bounds[c + 1] - bounds[c]);
       if (!n) continue;
+      const auto t_copy = std::chrono::steady_clock::now();
       SEQALK_CUDA(cudaSetDevice(0));
       SEQALK_CUDA(cudaMemcpy(penalties + lo, pen0 + lo, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
       SEQALK_CUDA(cudaMemcpy(digests.data() + 64 * lo, dig0 + 64 * lo, n * 64, cudaMemcpyDeviceToHost));
+      r.prof[4] += ms_since(t_copy);
       if (folder.joinable()) folder.join();
       mark("folding chunk", c);
       folder = std::thread([&, lo, n]() { fold_chain(digests.data() + 64 * lo, n, digest_hex, &hl); });
@@ -287,6 +298,7 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
   }
   if (folder.joinable()) folder.join();
   mark("folded");
+  r.prof[3] = ms_since(t_start) - r.prof[2];  // fold (and last copy) left exposed after the GPUs finished
   for (int d = 0; d < N; ++d) {
     try {
       r.workers[d]->finish_async();
@@ -296,6 +308,21 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
   }
   mark("GPUs idle");
   if (!error.empty()) throw std::runtime_error(error);
+  double kmax = 0, ksum = 0;
+  for (int d = 0; d < N; ++d) {
+    const JobStats &st = r.workers[d]->stats();
+    const double k = st.fill_ms + st.traceback_ms + st.digest_ms;
+    kmax = std::max(kmax, k);
+    ksum += k;
+    r.prof[9] += st.fill_ms;
+    r.prof[10] += st.traceback_ms;
+    r.prof[11] += st.digest_ms;
+  }
+  r.prof[0] = ms_since(t0);
+  r.prof[5] = kmax;
+  r.prof[6] = ksum / N;
+  r.prof[7] = N;
+  r.prof[8] = nchunks;
 }
 
 // all tasks of `tasks` on the runtime's GPUs; results in task order on the host
@@ -456,10 +483,25 @@ int seqalk_all_pairs(const char *const *seqs, const int32_t *lens, int32_t k, in
     all_tasks(k, tasks);
     if (r.workers.size() == 1) {
       // one GPU: results stream back batch by batch, the chain is folded under the GPU's shadow
+      const auto t0 = std::chrono::steady_clock::now();
+      auto ms_since = [&]() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      };
+      for (double &v : r.prof) v = 0;
       DeviceWorker &w = *r.workers[0];
       w.load(pack);
       w.plan(tasks, pxy, pgap);
+      r.prof[1] = ms_since();
       w.run_and_fold(penalties_out, digest_hex_out);
+      const JobStats &st = w.stats();
+      r.prof[0] = ms_since();
+      r.prof[2] = r.prof[0] - r.prof[1];
+      r.prof[5] = r.prof[6] = st.fill_ms + st.traceback_ms + st.digest_ms;
+      r.prof[7] = 1;
+      r.prof[8] = st.batches;
+      r.prof[9] = st.fill_ms;
+      r.prof[10] = st.traceback_ms;
+      r.prof[11] = st.digest_ms;
       return 0;
     }
     if (r.peer_ok) {
@@ -592,6 +634,14 @@ int seqalk_pair_score(const char *x, int32_t m, const char *y, int32_t n, int32_
   } catch (const std::exception &e) {
     return fail(e);
   }
+}
+
+int seqalk_profile(double *out, int32_t n) {
+  if (!out || n < 1) return fail("bad argument");
+  Runtime &r = rt();
+  std::lock_guard<std::mutex> g(r.mu);
+  for (int i = 0; i < n; ++i) out[i] = i < SEQALK_PROFILE_LEN ? r.prof[i] : 0.0;
+  return 0;
 }
 
 int64_t seqalk_num_tasks(int32_t k) { return k < 2 ? 0 : (int64_t)k * (k - 1) / 2; }

@@ -10,7 +10,7 @@
 namespace {
 
 enum Kind { K_LOP3 = 0, K_MIN3 = 1, K_IMAD = 2, K_MIXED = 3, K_ADDMIN = 4, K_SHF = 5, K_ALUMIN = 6, K_FILLMIX = 7,
-            K_DP4A = 8, K_DP4A_MIN3 = 9, K_DP4A_IMAD = 10, K_PRMT = 11 };
+            K_DP4A = 8, K_DP4A_MIN3 = 9, K_DP4A_IMAD = 10, K_PRMT = 11, K_MAX3U16 = 12, K_FILL16MIX = 13, K_DP4A_MIN3_DISTINCT = 14 };
 
 template <int KIND>
 __global__ void __launch_bounds__(256) issue_kernel(int *out, int iters, int a, int b) {
@@ -22,6 +22,11 @@ __global__ void __launch_bounds__(256) issue_kernel(int *out, int iters, int a, 
 #define DP4A(r) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b))
 #define PRMT(r) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(r) : "r"(a), "r"(b))
 #define MAD(r) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(r) : "r"(a), "r"(b))
+#define MAX3U(r, x, y) asm volatile("{.reg .b32 t; max.u16x2 t, %0, %1; max.u16x2 %0, t, %2;}" : "+r"(r) : "r"(x), "r"(y))
+#define PRMT3(d, x, y) asm volatile("prmt.b32 %0, %1, %2, %0;" : "+r"(d) : "r"(x), "r"(y))
+#define MADU(d, x) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(x), "r"(b))
+#define DP4A3(d, x, y) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(d) : "r"(x), "r"(y))
+#define MIN33(d, x, y) asm volatile("{.reg .s32 t; min.s32 t, %0, %1; min.s32 %0, t, %2;}" : "+r"(d) : "r"(x), "r"(y))
 #define ROW(OP) OP(r0); OP(r1); OP(r2); OP(r3); OP(r4); OP(r5); OP(r6); OP(r7)
   for (int i = 0; i < iters; ++i) {
     if (KIND == K_LOP3) { ROW(ALU); ROW(ALU); ROW(ALU); ROW(ALU); }
@@ -36,6 +41,34 @@ __global__ void __launch_bounds__(256) issue_kernel(int *out, int iters, int a, 
     if (KIND == K_DP4A_MIN3) { ROW(DP4A); ROW(MIN3); ROW(DP4A); ROW(MIN3); }
     if (KIND == K_DP4A_IMAD) { ROW(DP4A); ROW(MAD); ROW(DP4A); ROW(MAD); }
     if (KIND == K_PRMT) { ROW(PRMT); ROW(PRMT); ROW(PRMT); ROW(PRMT); }
+    if (KIND == K_MAX3U16) {  // VIMNMX3.U16x2, three different registers each
+      MAX3U(r0, r1, r2); MAX3U(r3, r4, r5); MAX3U(r6, r7, r0); MAX3U(r1, r2, r3);
+      MAX3U(r4, r5, r6); MAX3U(r7, r0, r1); MAX3U(r2, r3, r4); MAX3U(r5, r6, r7);
+      MAX3U(r0, r2, r4); MAX3U(r1, r3, r5); MAX3U(r6, r0, r2); MAX3U(r7, r1, r3);
+      MAX3U(r4, r6, r0); MAX3U(r5, r7, r1); MAX3U(r2, r4, r6); MAX3U(r3, r5, r7);
+      MAX3U(r0, r3, r6); MAX3U(r1, r4, r7); MAX3U(r2, r5, r0); MAX3U(r3, r6, r1);
+      MAX3U(r4, r7, r2); MAX3U(r5, r0, r3); MAX3U(r6, r1, r4); MAX3U(r7, r2, r5);
+      MAX3U(r0, r5, r2); MAX3U(r1, r6, r3); MAX3U(r2, r7, r4); MAX3U(r3, r0, r5);
+      MAX3U(r4, r1, r6); MAX3U(r5, r2, r7); MAX3U(r6, r3, r0); MAX3U(r7, r4, r1);
+    }
+    if (KIND == K_FILL16MIX) {  // the packed fill's mix, different registers: PRMT + IMAD + VIMNMX3.U16x2 (x 10, + 2)
+      PRMT3(r0, r1, r2); MADU(r3, r4); MAX3U(r5, r6, r7); PRMT3(r1, r2, r3); MADU(r4, r5); MAX3U(r6, r7, r0);
+      PRMT3(r2, r3, r4); MADU(r5, r6); MAX3U(r7, r0, r1); PRMT3(r3, r4, r5); MADU(r6, r7); MAX3U(r0, r1, r2);
+      PRMT3(r4, r5, r6); MADU(r7, r0); MAX3U(r1, r2, r3); PRMT3(r5, r6, r7); MADU(r0, r1); MAX3U(r2, r3, r4);
+      PRMT3(r6, r7, r0); MADU(r1, r2); MAX3U(r3, r4, r5); PRMT3(r7, r0, r1); MADU(r2, r3); MAX3U(r4, r5, r6);
+      PRMT3(r0, r2, r4); MADU(r5, r7); MAX3U(r1, r3, r6); PRMT3(r1, r3, r5); MADU(r6, r0); MAX3U(r2, r4, r7);
+      PRMT3(r3, r6, r1); MAX3U(r4, r7, r2);
+    }
+    if (KIND == K_DP4A_MIN3_DISTINCT) {  // the 32-bit fill's mix with three different registers per instruction
+      DP4A3(r0, r1, r2); MIN33(r3, r4, r5); DP4A3(r6, r7, r0); MIN33(r1, r2, r3);
+      DP4A3(r4, r5, r6); MIN33(r7, r0, r1); DP4A3(r2, r3, r4); MIN33(r5, r6, r7);
+      DP4A3(r0, r2, r4); MIN33(r1, r3, r5); DP4A3(r6, r0, r2); MIN33(r7, r1, r3);
+      DP4A3(r4, r6, r0); MIN33(r5, r7, r1); DP4A3(r2, r4, r6); MIN33(r3, r5, r7);
+      DP4A3(r0, r3, r6); MIN33(r1, r4, r7); DP4A3(r2, r5, r0); MIN33(r3, r6, r1);
+      DP4A3(r4, r7, r2); MIN33(r5, r0, r3); DP4A3(r6, r1, r4); MIN33(r7, r2, r5);
+      DP4A3(r0, r5, r2); MIN33(r1, r6, r3); DP4A3(r2, r7, r4); MIN33(r3, r0, r5);
+      DP4A3(r4, r1, r6); MIN33(r5, r2, r7); DP4A3(r6, r3, r0); MIN33(r7, r4, r1);
+    }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
 }
@@ -66,7 +99,7 @@ double run_kind(int sm_count, int *d_out) {
 
 }  // namespace
 
-extern "C" int seqalk_measure_int_peaks(int32_t device, double rates_out[12]) {
+extern "C" int seqalk_measure_int_peaks(int32_t device, double rates_out[16]) {
   if (!rates_out) return 1;
   if (cudaSetDevice(device) != cudaSuccess) return 1;
   cudaDeviceProp prop;
@@ -86,6 +119,10 @@ extern "C" int seqalk_measure_int_peaks(int32_t device, double rates_out[12]) {
   rates_out[9] = run_kind<K_DP4A_MIN3>(sms, d_out);
   rates_out[10] = run_kind<K_DP4A_IMAD>(sms, d_out);
   rates_out[11] = run_kind<K_PRMT>(sms, d_out);
+  rates_out[12] = run_kind<K_MAX3U16>(sms, d_out);
+  rates_out[13] = run_kind<K_FILL16MIX>(sms, d_out);
+  rates_out[14] = run_kind<K_DP4A_MIN3_DISTINCT>(sms, d_out);
+  rates_out[15] = 0;
   cudaFree(d_out);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
