@@ -233,9 +233,9 @@ def fill_kernel_model(stats, peaks):
                                      bound (2 instructions per cell at the measured dual-issue rate);
       directions-mode fill:          per cell VIMNMX3 + 2 SHF on the ALU pipe (3 per cell)."""
     if stats.get("fill_packed16"):
-        return {"bound": "alu_pipe", "ops_per_cell": 1.0, "peak": peaks["vimnmx3.u16x2"],
-                "peak_source": "measured live: VIMNMX3.U16x2 issue rate with three different register operands "
-                               "(seqalk_measure_int_peaks[12]) = the ALU pipe, 64 lanes/clk/SM",
+        return {"bound": "alu_pipe", "ops_per_cell": 1.0, "peak": peaks["vimnmx3"],
+                "peak_source": "measured live: VIMNMX3 issue rate "
+                               "(seqalk_measure_int_peaks[1]) = the ALU pipe, 64 lanes/clk/SM (PRMT, LOP3, SHF measure the same)",
                 "kernel": "fill16_kernel<16,6> (two DP cells per register)",
                 "sass": "per 2 cells: PRMT (ALU) + IMAD (FMA) + VIMNMX3.U16x2 (ALU); profiles/r02_fill16_sass.txt"}
     if stats.get("tile_mode"):
