@@ -161,7 +161,7 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
   int4 *__restrict__ keepB = reinterpret_cast<int4 *>(bbase + (uint64_t)(rowB0 / TILE_ROWS) * bstride);
   // column checkpoints: image (k, half) = mpad/2 packed words; this lane's RP words start at
   // row_base/2 + lane*RP (strip pairs are laid out one after the other)
-  const uint64_t halfwords = (uint64_t)P.mpad / 2;
+  const int halfwords = (int)(P.mpad / 2);
   uint32_t *__restrict__ ck = reinterpret_cast<uint32_t *>(a.dirs + P.dir_off) + (uint64_t)(row_base / 2 + lane * RP);
   // base log of this strip pair, behind the pair's kept rows
   const int nbl = base_log_entries(nq, KS);
@@ -275,14 +275,14 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
                      "r"(b0), "r"(b1), "r"(b2), "r"(b3), "r"(qcB), "r"(nq_keep)
                      : "memory");
       }
-      // ---- column checkpoints: the packed registers as they are (one lane at a time takes this)
+      // ---- column checkpoints: the packed registers as they are.  One lane at a time takes this
+      // branch (every lane once per 32 steps), so it is kept short: consecutive stores of a lane go
+      // to consecutive images (k, low halves), (k, high halves), (k+1, low halves), ...
       if (((qcA + 1) & 31) == 0) {
         const int ckcol = (qcA + 1) >> 5;  // even: the low halves are at a checkpoint column, odd: the high halves
-        const int half = ckcol & 1;
-        const int k = (ckcol >> 1) - 1;  // checkpoint index of that half's column
-        const int qc = half ? qcA - 32 : qcA;
-        if (k >= 0 && qc >= 0 && qc < nq) {
-          uint32_t *dst = ck + ((uint64_t)k * 2 + half) * halfwords;
+        const int qc = (ckcol & 1) ? qcA - 32 : qcA;
+        if (ckcol >= 2 && qc < nq) {
+          uint32_t *dst = ck + (int64_t)(ckcol - 2) * (int64_t)halfwords;
 #pragma unroll
           for (int r8 = 0; r8 < RP / 8; ++r8)
             asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * r8), "r"(h[8 * r8]),
