@@ -95,9 +95,9 @@ int seqalk_partition_all(const int32_t *lens, int32_t k, int64_t id_begin, int64
                          int64_t *ids_out, int64_t *counts_out);
 
 /* Chunk boundaries for `ntasks` tasks: bounds_out[nchunks+1], chunk c = ids
- * [bounds[c], bounds[c+1]).  Equal chunks, except that with >= 4 chunks (and >= 4096 tasks) the
- * last chunk holds only 4 % of the tasks, so that its fold — the only part of the hash chain that
- * cannot overlap GPU work — stays short. */
+ * [bounds[c], bounds[c+1]).  Equal chunks, except that with >= 5 chunks (and >= 4096 tasks) the
+ * last three hold 8 %, 5 % and 3 % of the tasks (with 4 chunks: a 4 % last chunk), so that the part
+ * of the serial hash-chain fold that cannot overlap GPU work stays short. */
 int seqalk_chunk_bounds(int64_t ntasks, int32_t nchunks, int64_t *bounds_out);
 /* The shards of the `nchunks` id ranges of seqalk_chunk_bounds for every rank, computed in
  * parallel: ids_out (capacity T) = chunk 0 rank 0, chunk 0 rank 1,

@@ -154,13 +154,22 @@ struct DeviceArray {
   }
 };
 
-// Chunk c covers task ids [bounds[c], bounds[c+1]).  With >= 4 chunks (and a large job) the
-// last chunk holds only 4 % of the tasks: the fold of the final chunk is the only part of the
-// hash chain that cannot hide under GPU work, so it is kept short — but not split further,
-// because very small chunks cost more in kernel tails than their fold saves (measured at 8 GPUs).
+// Chunk c covers task ids [bounds[c], bounds[c+1]).  The host folds chunk c (about 0.75 us per task,
+// serial by construction) while the GPUs work on the chunks after it; what stays exposed at the end
+// is  max over c of  fold(chunks >= c) - gpu(chunks > c).  Equal chunks leave the whole last
+// chunk's fold exposed; with >= 5 chunks (and >= 4096 tasks) the last three hold 8 %, 5 % and 3 % of
+// the tasks, which keeps the backlog below the last chunk's own fold up to 8 GPUs (the GPUs then
+// need about 1.3 us per task).  With 4 chunks: a 4 % last chunk.
 void chunk_bounds(int64_t T, int nchunks, std::vector<int64_t> &b) {
   b.assign((size_t)nchunks + 1, 0);
-  if (nchunks >= 4 && T >= 4096) {
+  if (nchunks >= 5 && T >= 4096) {
+    const int body = nchunks - 3;
+    const int64_t t3 = T * 3 / 100, t5 = T * 5 / 100, t8 = T * 8 / 100;
+    const int64_t body_total = T - t3 - t5 - t8;
+    for (int c = 0; c <= body; ++c) b[c] = body_total * c / body;
+    b[body + 1] = body_total + t8;
+    b[body + 2] = body_total + t8 + t5;
+  } else if (nchunks >= 4 && T >= 4096) {
     const int body = nchunks - 1;
     const int64_t body_total = T - T * 4 / 100;
     for (int c = 0; c <= body; ++c) b[c] = body_total * c / body;
@@ -198,7 +207,7 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
                     char digest_hex[129]) {
   const int N = (int)r.workers.size();
   const int64_t T = (int64_t)k * (k - 1) / 2;
-  int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(8, T / 32768));
+  int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(9, T / 32768));
   if (const char *e = std::getenv("SEQALK_PEER_CHUNKS"))  // tests: force several chunks on small jobs
     nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(64, T), std::atoi(e)));
   // SEQALK_TRACE=1: phase times of this call on stderr

@@ -214,6 +214,7 @@ DeviceWorker::DeviceWorker(int device) : dev_(device) {
   SEQALK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   SEQALK_CUDA(cudaStreamCreateWithPriority(&fill_stream_, cudaStreamNonBlocking, prio_lo));
   SEQALK_CUDA(cudaStreamCreateWithPriority(&post_stream_, cudaStreamNonBlocking, prio_hi));
+  SEQALK_CUDA(cudaStreamCreateWithPriority(&fill2_stream_, cudaStreamNonBlocking, prio_lo));
   for (Slot &s : slots_) {
     SEQALK_CUDA(cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
     SEQALK_CUDA(cudaEventCreateWithFlags(&s.fill_done, cudaEventDisableTiming));
@@ -249,6 +250,7 @@ DeviceWorker::~DeviceWorker() {
   }
   if (fill_stream_) cudaStreamDestroy(fill_stream_);
   if (post_stream_) cudaStreamDestroy(post_stream_);
+  if (fill2_stream_) cudaStreamDestroy(fill2_stream_);
   release(seq_);
   release(codes_);
   release(sel16_);
@@ -376,8 +378,13 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     SEQALK_CUDA(cudaSetDevice(dev_));
     size_t free_b = 0, total_b = 0;
     SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const int nbig = tiles_ ? 1 : nslots_;
-    double budget_gb = tiles_ ? 104.0 : 56.0;
+    // tile mode: the stages of a batch run back to back on one stream; with two pipelines (two
+    // sets of the big arrays, two streams) consecutive batches overlap, so the tail of one batch's
+    // fill / traceback / digest is filled by the next batch's kernels (SEQALK_OVERLAP=0: one set)
+    overlap_ = tiles_ && nslots_ >= 2;
+    if (const char *e = std::getenv("SEQALK_OVERLAP")) overlap_ = overlap_ && std::atoi(e) != 0;
+    const int nbig = tiles_ ? (overlap_ ? 2 : 1) : nslots_;
+    double budget_gb = tiles_ ? (overlap_ ? 52.0 : 104.0) : 56.0;
     if (const char *e = std::getenv("SEQALK_DIR_BUDGET_GB")) budget_gb = std::atof(e);
     dir_budget_ = (size_t)(budget_gb * (double)(1ull << 30));
     // our own (cached) buffers count as available
@@ -551,7 +558,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   ensure(check_, 2 * sizeof(uint32_t));
   if (batch_begin == 0) {
     const uint32_t init[2] = {0u, 0xffffffffu};
-    SEQALK_CUDA(cudaMemcpyAsync(check_.p, init, sizeof init, cudaMemcpyHostToDevice, fill_stream_));
+    SEQALK_CUDA(cudaMemcpy(check_.p, init, sizeof init, cudaMemcpyHostToDevice));  // before any stream's digest kernel
     stats_.self_checked = (!scores_only && corner_mode != CORNER_NONE) ? 1 : 0;
   }
   int32_t *h_pen = nullptr;
@@ -605,7 +612,9 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     Slot &S = slots_[b % nslots_];
     // tile mode: one stream, so one set of the big arrays serves every batch (the descriptor
     // buffers stay per slot: the host fills the next batch's staging while this one runs)
-    Slot &G = tiles_ ? slots_[0] : S;
+    Slot &G = (tiles_ && !overlap_) ? slots_[0] : S;
+    // the batch's stream (tile mode): its whole pipeline runs there
+    cudaStream_t tile_stream = (overlap_ && (b % nslots_) % 2 == 1) ? fill2_stream_ : fill_stream_;
     // ---- size device buffers (for the largest batch of the job: at most one allocation)
     ensure(S.pairs, need_.count * sizeof(PairDesc));
     ensure(S.tasks, (size_t)need_.nstrips * sizeof(StripTask));
@@ -688,7 +697,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     }
     S.last_pairs.assign(hp, hp + B.count);
     // ---- enqueue: fill stream
-    cudaStream_t st = fill_stream_;
+    cudaStream_t st = tiles_ ? tile_stream : fill_stream_;
     if (S.post_pending) {  // the slot's buffers are free once its previous batch is post-processed
       SEQALK_CUDA(cudaStreamWaitEvent(st, S.post_done, 0));
       S.post_pending = false;
@@ -741,7 +750,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     SEQALK_CUDA(cudaEventRecord(S.fill_done, st));
     // ---- enqueue: post stream (high priority; runs under the next batch's fill).  In tile
     // mode the traceback is a heavy kernel of its own: the stages run back to back instead.
-    st = tiles_ ? fill_stream_ : post_stream_;
+    st = tiles_ ? tile_stream : post_stream_;
     SEQALK_CUDA(cudaStreamWaitEvent(st, S.fill_done, 0));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 2], st));
 
@@ -807,6 +816,10 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     // chunk boundary: mark the chunk's results with an event and tell waiters
     for (size_t c = 0; c + 1 < chunk_batch_.size(); ++c)
       if (chunk_batch_[c + 1] == b + 1 && chunk_batch_[c + 1] > chunk_batch_[c]) {
+        // with two pipelines the chunk's earlier batches may still run on the other stream
+        if (overlap_)
+          for (Slot &O : slots_)
+            if (&O != &S && O.post_pending) SEQALK_CUDA(cudaStreamWaitEvent(st, O.post_done, 0));
         SEQALK_CUDA(cudaEventRecord(chunk_ev_[c], st));
         {
           std::lock_guard<std::mutex> g(async_mu_);
@@ -822,6 +835,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   if (streaming) fold_ready(true, batch_end);
   SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
   SEQALK_CUDA(cudaStreamSynchronize(post_stream_));
+  SEQALK_CUDA(cudaStreamSynchronize(fill2_stream_));
   for (Slot &S : slots_) S.staged_pending = S.post_pending = false;
   if (batch_end == batches_.size() && !scores_only) verify_check();
   ran_ = true;
@@ -911,7 +925,7 @@ bool DeviceWorker::fetch_alignment(size_t index_in_job, std::vector<uint8_t> &a1
   const Batch &B = batches_[b];
   if (index_in_job < B.first || index_in_job >= B.first + B.count) return false;
   Slot &S = slots_[b % nslots_];
-  Slot &G = tiles_ ? slots_[0] : S;
+  Slot &G = (tiles_ && !overlap_) ? slots_[0] : S;
   size_t p = 0;
   while (p < S.last_pairs.size() && (size_t)S.last_pairs[p].task_id != index_in_job) ++p;
   if (p == S.last_pairs.size()) return false;

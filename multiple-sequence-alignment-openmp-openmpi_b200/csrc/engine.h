@@ -145,6 +145,9 @@ class DeviceWorker {
   int nslots_ = 2;
   std::vector<Slot> slots_;
   cudaStream_t fill_stream_ = nullptr, post_stream_ = nullptr;
+  cudaStream_t fill2_stream_ = nullptr;  // tile mode with overlap: batches alternate between fill_stream_ and this one
+  bool overlap_ = false;  // tile mode: two full pipelines (buffer sets + streams), so that a batch's kernel tails are
+                          // filled by the next batch's kernels
   DevBuf seq_, codes_, sel16_, seqmeta_;
   const SeqPack *pack_ = nullptr;
   SeqPack pack_copy_;
