@@ -9,12 +9,13 @@ A step = one full all-pairs job (getMinimumPenalties) over the named synthetic w
 pair's DP fill + traceback + per-pair SHA-512 on the GPU(s), gather in the reference's task
 order, ordered hash chain on the host.
   value      cells / step time with the sequences resident in HBM and the batches planned; one
-             process per GPU, barrier + max over ranks (at N > 1: NCCL all_gather per chunk).
+             process per GPU, barrier + max over ranks (at N > 1 the 68-byte records are gathered
+             to rank 0 once per chunk: copy engine to pinned memory + gloo gather, no kernel launch).
   e2e        the same job through the drop-in C ABI call `seqalk_all_pairs` with HOST buffers (H2D of
              the inputs, D2H of penalties + digests, chain) in the timed region.  At N > 1 rank 0
              makes that one call with seqalk_init(N): one host thread per GPU, results gathered by
              peer stores over NVLink from the digest kernel (the fused path); the torchrun / NCCL
-             figure of the same job is kept as `e2e_nccl`.
+             figure of the same job is kept as `e2e_multiprocess`.
   parity     the GPU result on a bounded sample of the workload against the CPU arm (the
              unmodified reference build, or the oracle port) in the same run, plus the committed
              full-size oracle goldens; a mismatch makes the process exit non-zero.
@@ -310,7 +311,7 @@ def main():
         def step_resident():
             nonlocal result
             shard.start()
-            result = dmod.run_sharded(plan, rank, shard.run_chunk)
+            result = dmod.run_sharded(plan, rank, shard.run_chunk_host)  # host gather: no kernel behind the fill
             shard.finish()
 
         for _ in range(warmup):
@@ -367,7 +368,7 @@ def main():
         dir_rate = sum_over_ranks(dir_bytes / (fill_ms * 1e-3) if fill_ms > 0 else 0.0) / world
 
         # ---- e2e: host buffers in, host results out.  N = 1: the C ABI call.  N > 1: the torchrun /
-        # NCCL form here (kept as e2e_nccl); the C ABI call with seqalk_init(N) follows after teardown.
+        # form here (kept as e2e_multiprocess); the C ABI call with seqalk_init(N) follows after teardown.
         e2e_s, digest_e2e, pen_e2e = [], None, None
         for _ in range(steps):
             barrier()
@@ -449,7 +450,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": sum(M["lens"]) * world, "d2h_bytes_per_step": M["T"] * 68,
-                    "path": "seqalk_all_pairs (C ABI, host buffers)" if world == 1 else "torchrun + NCCL all_gather (see e2e_nccl; replaced below by the in-process call)"},
+                    "path": "seqalk_all_pairs (C ABI, host buffers)" if world == 1 else "one process per GPU (see e2e_multiprocess; replaced below by the in-process call)"},
             "gpu_launches": M["launches"],
             "roofline": {
                 "bound": model["bound"], "achieved": achieved, "peak": model["peak"] / 1e9, "unit": "G lane-instr/s",
@@ -510,7 +511,7 @@ def main():
                     times.append(time.perf_counter() - t0)
                 prof = pkg.last_profile()
                 in_ms = statistics.mean(times) * 1e3
-                line["e2e_nccl"] = dict(line["e2e"], path="one process per GPU (torchrun), NCCL all_gather per chunk, scatter + fold on rank 0")
+                line["e2e_multiprocess"] = dict(line["e2e"], path="one process per GPU (torchrun): records to pinned host memory by copy engine, gloo gather per chunk, scatter + fold on rank 0")
                 line["e2e"] = {"value": M["cells"] / (in_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": in_ms,
                                "h2d_bytes_per_step": sum(M["lens"]) * world, "d2h_bytes_per_step": M["T"] * 68,
                                "path": f"seqalk_init({world}) + seqalk_all_pairs (C ABI, host buffers): one host thread per GPU, "

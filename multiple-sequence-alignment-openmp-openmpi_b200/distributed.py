@@ -7,9 +7,19 @@ Triple{i,j,id} tasks one by one (:280-331), workers return Packet{penalty,id,has
 Here: every rank holds the inputs (replicated, as in the reference), the k(k-1)/2 tasks are
 sharded statically by cell count (LPT — independent units, no data-path collective during the
 fill), every rank runs its shard on its own GPU through the C ABI, and the per-task
-(penalty, 64-byte digest) records are gathered over NCCL/NVLink with one all_gather per chunk
-of task ids.  Rank 0 scatters them back into the reference's task order and folds the chain;
-with ``nchunks > 1`` the fold of chunk c overlaps the GPUs' work on chunk c+1.
+(penalty, 64-byte digest) records are gathered to rank 0 once per chunk of task ids.  Rank 0
+scatters them back into the reference's task order and folds the chain; with ``nchunks > 1`` the
+fold of chunk c overlaps the GPUs' work on chunk c+1.
+
+Two gathers (34 MB per k = 1000 job, so neither is a bandwidth question):
+* ``gather="host"`` (default on GPUs): each rank copies its chunk's records to pinned host memory
+  with the copy engine and the ranks meet in a gloo ``gather`` — no kernel is launched for the
+  hand-off.  The fill is a persistent kernel that owns every SM; a NCCL kernel queued behind it
+  would not get a CTA slot before the fill's tail (with the engine's overlapped batch pipelines
+  there is always a fill resident), which delayed every chunk by one fill in the measurements.
+* ``gather="nccl"``: ``all_gather_into_tensor`` over NVLink on the GPUs, kept for comparison.
+The single-process form (``seqalk_init(N)`` + ``seqalk_all_pairs``) gathers with peer stores from
+the digest kernel instead (csrc/api.cu).
 
 ``compute`` is injectable so that the shard/gather/reorder logic is testable on CPU with the
 gloo backend (tests/test_distributed_cpu.py); the default computes on the rank's GPU and
@@ -75,6 +85,11 @@ class GpuShard:
         # largest shard of the chunk so that one all_gather_into_tensor moves everything
         self.send = [torch.zeros((max(plan.max_count(c), 1), 68), dtype=torch.uint8, device=self.device)
                      for c in range(plan.nchunks)]
+        # host path: pinned mirrors of the result arrays + a copy stream (copy engine only)
+        self.h_pen = torch.zeros(max(self.n, 1), dtype=torch.int32).pin_memory()
+        self.h_dig = torch.zeros((max(self.n, 1), 64), dtype=torch.uint8).pin_memory()
+        self.h_send = [torch.zeros((max(plan.max_count(c), 1), 68), dtype=torch.uint8) for c in range(plan.nchunks)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
 
     def start(self):
         """Start every chunk (asynchronously, back to back on the GPU)."""
@@ -91,6 +106,24 @@ class GpuShard:
             self.send[c][:n, :4] = self.pen[lo:hi].view(self.torch.uint8).view(n, 4)
             self.send[c][:n, 4:] = self.dig[lo:hi]
         return self.send[c]
+
+    def run_chunk_host(self, c: int):
+        """Host form of run_chunk: waits for chunk c, copies its records device -> pinned host with
+        the copy engine (no kernel launch) and packs them into a CPU tensor (maxcount_c, 68)."""
+        lo, hi = int(self.starts[c]), int(self.ends[c])
+        n = hi - lo
+        buf = self.h_send[c]
+        if n:
+            torch = self.torch
+            self.job.wait_chunk(c, self.copy_stream.cuda_stream)
+            with torch.cuda.stream(self.copy_stream):
+                self.h_pen[lo:hi].copy_(self.pen[lo:hi], non_blocking=True)
+                self.h_dig[lo:hi].copy_(self.dig[lo:hi], non_blocking=True)
+            self.copy_stream.synchronize()
+            out = buf.numpy()
+            out[:n, :4] = self.h_pen[lo:hi].numpy().view(np.uint8).reshape(n, 4)
+            out[:n, 4:] = self.h_dig[lo:hi].numpy()
+        return buf
 
     def finish(self):
         if self.job is not None:
@@ -116,12 +149,31 @@ def _scatter(plan: ShardPlan, c: int, gathered: np.ndarray, penalties: np.ndarra
             digests[ids] = rec[:, 4:]
 
 
+_HOST_GROUPS = {}
+
+
+def host_group(group=None):
+    """A gloo group over the same ranks as ``group`` (created once; collective call)."""
+    import torch.distributed as dist
+
+    key = id(group) if group is not None else 0
+    if key not in _HOST_GROUPS:
+        if dist.get_backend(group) == "gloo":
+            _HOST_GROUPS[key] = group
+        else:
+            ranks = dist.get_process_group_ranks(group) if group is not None else None
+            _HOST_GROUPS[key] = dist.new_group(ranks=ranks, backend="gloo")
+    return _HOST_GROUPS[key]
+
+
 def run_sharded(plan: ShardPlan, rank: int, run_chunk: Callable[[int], "object"], group=None,
                 ) -> Optional[Tuple[str, np.ndarray]]:
-    """Drives the chunks: run, all_gather, and (rank 0) scatter + fold in task order.
+    """Drives the chunks: run, gather, and (rank 0) scatter + fold in task order.
 
-    ``run_chunk(c)`` returns a torch uint8 tensor (maxcount_c, 68) living on the device the
-    process group communicates on.  Returns (digest, penalties) on rank 0, None elsewhere."""
+    ``run_chunk(c)`` returns a torch uint8 tensor (maxcount_c, 68): on the device the process
+    group communicates on (NCCL / gloo ``all_gather_into_tensor``), or on the CPU while the group
+    is a GPU one (host gather: gloo ``gather`` to rank 0).  Returns (digest, penalties) on rank 0,
+    None elsewhere."""
     import torch
     import torch.distributed as dist
 
@@ -138,15 +190,24 @@ def run_sharded(plan: ShardPlan, rank: int, run_chunk: Callable[[int], "object"]
 
     for c in range(plan.nchunks):
         send = run_chunk(c)
-        if world > 1:
+        host = None
+        if world > 1 and send.device.type == "cpu" and dist.get_backend(group) != "gloo":
+            # host gather: the records are already in host memory on every rank
+            hg = host_group(group)
+            parts = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+            dist.gather(send, parts, dst=dist.get_global_rank(hg, 0), group=hg)
+            if rank == 0:
+                host = np.stack([p.numpy() for p in parts])
+        elif world > 1:
             rows = send.shape[0]
             flat = torch.empty((world * rows, send.shape[1]), dtype=send.dtype, device=send.device)
             dist.all_gather_into_tensor(flat, send.contiguous(), group=group)
             recv = flat.view(world, rows, send.shape[1])
-        else:
-            recv = send.unsqueeze(0)
+            if rank == 0:
+                host = recv.cpu().numpy()  # D2H of the gathered records (synchronises the stream)
+        elif rank == 0:
+            host = send.unsqueeze(0).cpu().numpy()
         if rank == 0:
-            host = recv.cpu().numpy()  # D2H of the gathered records (synchronises the stream)
             if folder is not None:
                 folder.join()
             folder = threading.Thread(target=fold_range, args=(c, host))
@@ -160,7 +221,7 @@ def run_sharded(plan: ShardPlan, rank: int, run_chunk: Callable[[int], "object"]
 
 def all_pairs_distributed(genes: Sequence[bytes], pxy: int, pgap: int, *, nchunks: int = 1, group=None,
                           device: Optional[int] = None, compute: Optional[ComputeFn] = None,
-                          ) -> Optional[Tuple[str, np.ndarray]]:
+                          gather: str = "host") -> Optional[Tuple[str, np.ndarray]]:
     """getMinimumPenalties over all ranks of the default process group.
 
     Every rank passes the same inputs.  Returns (digest, penalties) on rank 0, None elsewhere."""
@@ -178,7 +239,7 @@ def all_pairs_distributed(genes: Sequence[bytes], pxy: int, pgap: int, *, nchunk
         shard = GpuShard(genes, pxy, pgap, plan, rank, dev)
         try:
             shard.start()
-            res = run_sharded(plan, rank, shard.run_chunk, group)
+            res = run_sharded(plan, rank, shard.run_chunk_host if gather == "host" else shard.run_chunk, group)
             shard.finish()
             return res
         finally:

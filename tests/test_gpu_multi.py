@@ -1,4 +1,5 @@
-"""GPU, 2 ranks (one process per GPU, NCCL): digest identical to the oracle and to 1 GPU."""
+"""GPU, 2 ranks (one process per GPU; records gathered through pinned host memory + gloo, and
+through NCCL for comparison): digest identical to the oracle and to 1 GPU."""
 import os
 import socket
 import subprocess
@@ -20,12 +21,14 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 dmod = importlib.import_module(PKG + ".distributed")
 workloads = importlib.import_module(PKG + ".workloads")
 genes = workloads.mixed(20, seed=77, lo=300, hi=4000)
-res = dmod.all_pairs_distributed(genes, 3, 2, nchunks=3, device=local)
+res = dmod.all_pairs_distributed(genes, 3, 2, nchunks=3, device=local)            # host gather (gloo)
+res2 = dmod.all_pairs_distributed(genes, 3, 2, nchunks=2, device=local, gather="nccl")  # NCCL all_gather
 if rank == 0:
     from oracle import binding as oracle
     od, op, _ = oracle.all_pairs(genes, 3, 2)
     assert res[0] == od, (res[0], od)
     assert np.array_equal(res[1], op)
+    assert res2[0] == od and np.array_equal(res2[1], op)
     print("MULTI_OK", res[0][:16])
 dist.destroy_process_group()
 '''
