@@ -1,6 +1,11 @@
 // sha512_host.cpp — see sha512_host.h
 #include "sha512_host.h"
 
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
 namespace seqalk {
 
 namespace {
@@ -38,8 +43,32 @@ inline void store_be64(uint8_t *p, uint64_t v) {
 }
 }  // namespace
 
-void Sha512::compress(uint64_t st[8], const uint8_t *block) {
+// The compression function in two halves, so that the fold below can take the message schedule
+// of a block (which does not depend on the chain state) off the serial path:
+//   schedule_kw: kw[t] = K[t] + W[t], t = 0..79, from the 128 message bytes;
+//   rounds_kw:   the 80 rounds on precomputed kw.
+// target_clones: a BMI2 (RORX) build of the same code, picked at load time on CPUs that have it.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define SEQALK_CLONES __attribute__((target_clones("default", "bmi2")))
+#else
+#define SEQALK_CLONES
+#endif
+
+SEQALK_CLONES void schedule_kw(const uint8_t *block, uint64_t kw[80]) {
   uint64_t w[16];
+  for (int t = 0; t < 16; ++t) {
+    w[t] = load_be64(block + 8 * t);
+    kw[t] = w[t] + K[t];
+  }
+  for (int t0 = 16; t0 < 80; t0 += 16)
+    for (int k = 0; k < 16; ++k) {
+      const uint64_t w15 = w[(k + 1) & 15], w2 = w[(k + 14) & 15];
+      w[k] += (rotr(w15, 1) ^ rotr(w15, 8) ^ (w15 >> 7)) + w[(k + 9) & 15] + (rotr(w2, 19) ^ rotr(w2, 61) ^ (w2 >> 6));
+      kw[t0 + k] = w[k] + K[t0 + k];
+    }
+}
+
+SEQALK_CLONES void rounds_kw(uint64_t st[8], const uint64_t kw[80]) {
   uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #define SEQALK_ROUND(a, b, c, d, e, f, g, h, kw)                                     \
   {                                                                                  \
@@ -48,6 +77,22 @@ void Sha512::compress(uint64_t st[8], const uint8_t *block) {
     d += t1;                                                                         \
     h = t1 + t2;                                                                     \
   }
+  for (int k = 0; k < 80; k += 8) {
+    SEQALK_ROUND(a, b, c, d, e, f, g, h, kw[k + 0]);
+    SEQALK_ROUND(h, a, b, c, d, e, f, g, kw[k + 1]);
+    SEQALK_ROUND(g, h, a, b, c, d, e, f, kw[k + 2]);
+    SEQALK_ROUND(f, g, h, a, b, c, d, e, kw[k + 3]);
+    SEQALK_ROUND(e, f, g, h, a, b, c, d, kw[k + 4]);
+    SEQALK_ROUND(d, e, f, g, h, a, b, c, kw[k + 5]);
+    SEQALK_ROUND(c, d, e, f, g, h, a, b, kw[k + 6]);
+    SEQALK_ROUND(b, c, d, e, f, g, h, a, kw[k + 7]);
+  }
+  st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+SEQALK_CLONES void compress_block(uint64_t st[8], const uint8_t *block) {
+  uint64_t w[16];
+  uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
   for (int t = 0; t < 16; ++t) w[t] = load_be64(block + 8 * t);
   for (int t0 = 0; t0 < 80; t0 += 16) {
     if (t0) {
@@ -71,6 +116,8 @@ void Sha512::compress(uint64_t st[8], const uint8_t *block) {
 #undef SEQALK_ROUND
   st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
+
+void Sha512::compress(uint64_t st[8], const uint8_t *block) { compress_block(st, block); }
 
 void Sha512::reset() {
   st_[0] = 0x6a09e667f3bcc908ULL; st_[1] = 0xbb67ae8584caa73bULL; st_[2] = 0x3c6ef372fe94f82bULL;
@@ -125,18 +172,96 @@ void Sha512::hex(const void *data, size_t len, char out[129]) {
   out[128] = 0;
 }
 
-void fold_chain(const uint8_t *pair_digests, size_t count, char state_hex[129], size_t *hex_len) {
-  // message = H_t (0 or 128 chars) ++ hex(pair digest) (128 chars); the padding block of a
-  // 256-byte message is constant.
-  uint8_t msg[256 + 128];
-  size_t hl = *hex_len;
-  if (hl) std::memcpy(msg, state_hex, 128);
-  for (size_t t = 0; t < count; ++t) {
-    hex128(pair_digests + 64 * t, reinterpret_cast<char *>(msg) + hl);
+namespace {
+const uint64_t IV[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                        0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+constexpr size_t FOLD_BLOCK = 512;  // tasks per hand-over between the schedule thread and the chain
+
+// kw of the padding block of a 256-byte message (0x80, zeros, bit length 2048): constant
+struct PadKw {
+  uint64_t kw[80];
+  PadKw() {
+    uint8_t pad[128];
+    std::memset(pad, 0, sizeof pad);
+    pad[0] = 0x80;
+    store_be64(pad + 120, 256ull * 8);
+    schedule_kw(pad, kw);
+  }
+};
+
+// the chain step for tasks [t0, t1) given the schedules of their second blocks (hex of the pair digest)
+void fold_steps(const uint64_t *kw2, size_t n, uint8_t msg_state[128]) {
+  static const PadKw pad;
+  for (size_t t = 0; t < n; ++t) {
+    uint64_t st[8];
+    std::memcpy(st, IV, sizeof st);
+    compress_block(st, msg_state);        // block 1 = hex(H_t): the only schedule on the serial path
+    rounds_kw(st, kw2 + 80 * t);          // block 2 = hex(problemhash_t)
+    rounds_kw(st, pad.kw);                // block 3 = padding
     uint8_t r[64];
-    Sha512::raw(msg, hl + 128, r);
+    for (int i = 0; i < 8; ++i) store_be64(r + 8 * i, st[i]);
+    hex128(r, reinterpret_cast<char *>(msg_state));
+  }
+}
+}  // namespace
+
+void fold_chain(const uint8_t *pair_digests, size_t count, char state_hex[129], size_t *hex_len) {
+  // message = H_t (0 or 128 chars) ++ hex(pair digest) (128 chars).  For H_t != "" the message is
+  // three blocks: hex(H_t) | hex(pair digest) | constant padding.  Only the first block's message
+  // schedule depends on the chain; the second block's schedules are computed FOLD_BLOCK tasks
+  // ahead by a helper thread (they cost about a third of a compression), the third's is constant.
+  size_t hl = *hex_len;
+  uint8_t msg[128];
+  size_t t = 0;
+  if (hl == 0 && count) {  // first step of the chain: a 128-byte message
+    char hexd[128];
+    hex128(pair_digests, hexd);
+    uint8_t r[64];
+    Sha512::raw(hexd, 128, r);
     hex128(r, reinterpret_cast<char *>(msg));
     hl = 128;
+    t = 1;
+  } else if (hl) {
+    std::memcpy(msg, state_hex, 128);
+  }
+  const size_t rest = count - t;
+  if (rest) {
+    auto schedules = [&](size_t first, size_t n, uint64_t *kw2) {
+      char hexd[128];
+      for (size_t i = 0; i < n; ++i) {
+        hex128(pair_digests + 64 * (first + i), hexd);
+        schedule_kw(reinterpret_cast<const uint8_t *>(hexd), kw2 + 80 * i);
+      }
+    };
+    if (rest < 4 * FOLD_BLOCK) {  // short: no thread
+      std::vector<uint64_t> kw2(80 * std::min(rest, FOLD_BLOCK));
+      for (size_t done = 0; done < rest; done += FOLD_BLOCK) {
+        const size_t n = std::min(FOLD_BLOCK, rest - done);
+        schedules(t + done, n, kw2.data());
+        fold_steps(kw2.data(), n, msg);
+      }
+    } else {
+      // ring of 4 blocks: the helper fills block b while the chain consumes block b - 1 ... b - 3
+      constexpr size_t RING = 4;
+      std::vector<uint64_t> kw2(80 * FOLD_BLOCK * RING);
+      const size_t nblocks = (rest + FOLD_BLOCK - 1) / FOLD_BLOCK;
+      std::atomic<size_t> produced{0}, consumed{0};
+      std::thread helper([&]() {
+        for (size_t b = 0; b < nblocks; ++b) {
+          while (b >= consumed.load(std::memory_order_acquire) + RING) std::this_thread::yield();
+          const size_t n = std::min(FOLD_BLOCK, rest - b * FOLD_BLOCK);
+          schedules(t + b * FOLD_BLOCK, n, kw2.data() + 80 * FOLD_BLOCK * (b % RING));
+          produced.store(b + 1, std::memory_order_release);
+        }
+      });
+      for (size_t b = 0; b < nblocks; ++b) {
+        while (produced.load(std::memory_order_acquire) <= b) std::this_thread::yield();
+        const size_t n = std::min(FOLD_BLOCK, rest - b * FOLD_BLOCK);
+        fold_steps(kw2.data() + 80 * FOLD_BLOCK * (b % RING), n, msg);
+        consumed.store(b + 1, std::memory_order_release);
+      }
+      helper.join();
+    }
   }
   if (hl) std::memcpy(state_hex, msg, 128);
   state_hex[hl] = 0;
