@@ -422,7 +422,15 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   // 16x2-packed fill (fill16.cu): tile mode, cost table, 1024 / 512-row strip pairs (the geometry
   // of the 32-rows-per-lane fill), penalties small enough for 16-bit relative scores
   fill16_shift_ = 0;
-  if (tiles_ && variant_.mode == MODE_TAB && variant_.R == 32 && mixed_ && codes_.p) fill16_shift_ = fill16_rebase_shift(pxy, pgap);
+  main_rp_ = 32;  // 2048-row strip pairs (+ 1024 / 512-row tails): less bookkeeping per cell than 1024-row ones
+  if (const char *e = std::getenv("SEQALK_FILL16_RP")) main_rp_ = std::atoi(e) == 16 ? 16 : 32;
+  if (tiles_ && variant_.mode == MODE_TAB && variant_.R == 32 && mixed_ && codes_.p) {
+    fill16_shift_ = fill16_rebase_shift(pxy, pgap, main_rp_);
+    if (!fill16_shift_ && main_rp_ == 32) {
+      main_rp_ = 16;
+      fill16_shift_ = fill16_rebase_shift(pxy, pgap, main_rp_);
+    }
+  }
   if (const char *e = std::getenv("SEQALK_FILL16"))
     if (!std::atoi(e)) fill16_shift_ = 0;
   const int R = variant_.R;
@@ -447,7 +455,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     // an empty sequence (undefined in the parallel reference: ceil(0/0) tile size at
     // submit/xuliny-seqalkway.cpp:457; the sequential twin :570-663 returns (m+n)*pgap with a
     // pure-tail alignment) has no DP cells: no strips, the traceback only writes the tails
-    StripGeom geo = strip_geometry(m, R, mixed_);
+    StripGeom geo = geometry(m);
     if (m < 1 || n < 1) geo.nstrips = 0, geo.half_last = 0;
     const uint32_t ns = (uint32_t)geo.nstrips;
     uint64_t brow_ints = tiles_ ? (uint64_t)(geo.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(n) + 4)
@@ -487,7 +495,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   }
   stats_.tile_mode = tiles_ ? 1 : 0;
   stats_.fill_packed16 = fill16_shift_ ? 1 : 0;
-  stats_.fill_rows_per_lane = (uint32_t)variant_.R;
+  stats_.fill_rows_per_lane = fill16_shift_ ? (uint32_t)main_rp_ : (uint32_t)variant_.R;
   // buffer sizes: the largest batch decides, so that run() never reallocates mid-job
   need_ = Batch{0, 0, 0, 0, 0, 0, 0};
   for (const Batch &b : batches_) {
@@ -625,7 +633,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ensure(G.out, need_.out_bytes + BUFFER_SLACK);
     ensure(G.align, need_.count * sizeof(PairAlign));
     ensure(G.cost, need_.count * sizeof(int32_t));
-    ensure(S.counter, 2 * sizeof(uint32_t));
+    ensure(S.counter, 4 * sizeof(uint32_t));
     // ---- build descriptors in pinned staging
     const size_t pairs_bytes = round_up(need_.count * sizeof(PairDesc), 256);
     const size_t tasks_bytes = round_up((size_t)need_.nstrips * sizeof(StripTask), 256);
@@ -662,7 +670,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       d.brow_off = brow_off;
       d.out_off = out_off;
       d.strip0 = strip0;
-      StripGeom geo = strip_geometry(d.m, R, mixed_);
+      StripGeom geo = geometry(d.m);
       if (d.m < 1 || d.n < 1) geo.nstrips = 0, geo.half_last = 0;
       d.nstrips = geo.nstrips;
       d.mpad = geo.mpad;
@@ -684,16 +692,19 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       max_strips = std::max(max_strips, d.nstrips);
     }
     // strip queue ordered (strip, pair): a strip's predecessor is always claimed earlier.
-    // Half-height last strips (tile mode) go to the end: they run in a second launch with the
-    // 16-rows-per-lane kernel, after all their predecessors have finished.
-    size_t n_main = 0, n_half = 0;
+    // Shorter last strips (tile mode) go to the end: they run in later launches (1024-row strip
+    // pairs of the three-level geometry with 16 rows per half lane, then the 512-row ones), after
+    // all their predecessors have finished.
+    size_t n_main = 0, n_mid = 0, n_half = 0;
     {
       for (int s = 0; s < max_strips; ++s)
         for (size_t p = 0; p < B.count; ++p)
-          if (s < hp[p].nstrips && !(hp[p].half_last && s == hp[p].nstrips - 1))
-            ht[n_main++] = StripTask{(uint32_t)p, (uint32_t)s};
+          if (s < main_strips(hp[p].nstrips, hp[p].half_last)) ht[n_main++] = StripTask{(uint32_t)p, (uint32_t)s};
       for (size_t p = 0; p < B.count; ++p)
-        if (hp[p].half_last) ht[n_main + n_half++] = StripTask{(uint32_t)p, (uint32_t)(hp[p].nstrips - 1)};
+        if (hp[p].half_last & 2)
+          ht[n_main + n_mid++] = StripTask{(uint32_t)p, (uint32_t)main_strips(hp[p].nstrips, hp[p].half_last)};
+      for (size_t p = 0; p < B.count; ++p)
+        if (hp[p].half_last & 1) ht[n_main + n_mid + n_half++] = StripTask{(uint32_t)p, (uint32_t)(hp[p].nstrips - 1)};
     }
     S.last_pairs.assign(hp, hp + B.count);
     // ---- enqueue: fill stream
@@ -707,7 +718,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     SEQALK_CUDA(cudaMemcpyAsync(S.slots.p, hs, B.count * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SEQALK_CUDA(cudaEventRecord(S.staged, st));
     S.staged_pending = true;
-    SEQALK_CUDA(cudaMemsetAsync(S.counter.p, 0, 2 * sizeof(uint32_t), st));
+    SEQALK_CUDA(cudaMemsetAsync(S.counter.p, 0, 4 * sizeof(uint32_t), st));
     SEQALK_CUDA(cudaMemsetAsync(S.progress.p, 0, (size_t)B.nstrips * sizeof(uint32_t), st));
 
     FillArgs fa;
@@ -726,14 +737,23 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.pgap = pgap_;
     fa.sel16 = static_cast<const uint8_t *>(sel16_.p);
     fa.rebase_shift = fill16_shift_;
+    fa.main_rp = main_rp_;
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 0], st));
     if (fill16_shift_)
-      SEQALK_CUDA(launch_fill16(fa, 16, variant_.minb, sm_count_, st));
+      SEQALK_CUDA(launch_fill16(fa, main_rp_, variant_.minb, sm_count_, st));
     else
       SEQALK_CUDA(launch_fill(fa, variant_, sm_count_, st));
-    if (n_half) {  // second launch: the 512-row last strips
+    if (n_mid) {  // second launch (three-level geometry): the 1024-row strip pairs
+      FillArgs fm = fa;
+      fm.tasks = fa.tasks + n_main;
+      fm.ntasks = (uint32_t)n_mid;
+      fm.counter = fa.counter + 2;
+      SEQALK_CUDA(launch_fill16(fm, 16, 0, sm_count_, st));
+      stats_.fill_launches++;
+    }
+    if (n_half) {  // last launch: the 512-row last strips
       FillArgs fh = fa;
-      fh.tasks = fa.tasks + n_main;
+      fh.tasks = fa.tasks + n_main + n_mid;
       fh.ntasks = (uint32_t)n_half;
       fh.counter = fa.counter + 1;
       if (fill16_shift_) {
@@ -770,6 +790,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.mode = variant_.mode;
     ta.addmode = variant_.addmode;
     ta.ck16 = fill16_shift_;
+    ta.main_rows = 64 * main_rp_;
     ta.long_pairs = few_pairs_ ? 1 : 0;
     ta.strip_scan = strip_scan_ ? 1 : 0;
     if (const char *e = std::getenv("SEQALK_TB_LONG")) ta.long_pairs = std::atoi(e) ? 1 : 0;

@@ -159,6 +159,10 @@ class DeviceWorker {
   FillVariant variant_;
   bool few_pairs_ = false;  // fewer strips than ~2x the resident warps: wavefront-bound job
   bool mixed_ = false;  // tile mode, R = 32: half-height last strips (second fill launch)
+  int main_rp_ = 16;      // packed fill: rows per half lane of the main strip pairs (32: 2048-row strip pairs + 1024 / 512-row tails)
+  StripGeom geometry(int m) const {
+    return (fill16_shift_ && main_rp_ == 32) ? strip_geometry3(m) : strip_geometry(m, variant_.R, mixed_);
+  }
   int fill16_shift_ = 0;  // > 0: the 16x2-packed fill (fill16.cu) runs the tile-mode fill; value = log2 of its re-base interval
   bool tiles_ = false;  // tile mode: score-only fill + checkpoints, directions recomputed per tile
   Batch need_{0, 0, 0, 0, 0, 0, 0};  // per-buffer maxima over the job's batches

@@ -132,8 +132,16 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
   {
     const uint8_t *__restrict__ xs = a.codes + P.x_off;  // zero padded far beyond m (engine.cu)
     unsigned wa[RP / 4], wb[RP / 4];
-    static_assert(RP == 16 || RP == 8, "rows per half lane");
-    if constexpr (RP == 16) {
+    static_assert(RP == 32 || RP == 16 || RP == 8, "rows per half lane");
+    if constexpr (RP == 32) {
+#pragma unroll
+      for (int q4 = 0; q4 < 2; ++q4) {
+        const uint4 va = rowA0 + 16 * q4 < m ? __ldg(reinterpret_cast<const uint4 *>(xs + rowA0) + q4) : make_uint4(0, 0, 0, 0);
+        const uint4 vb = rowB0 + 16 * q4 < m ? __ldg(reinterpret_cast<const uint4 *>(xs + rowB0) + q4) : make_uint4(0, 0, 0, 0);
+        wa[4 * q4] = va.x; wa[4 * q4 + 1] = va.y; wa[4 * q4 + 2] = va.z; wa[4 * q4 + 3] = va.w;
+        wb[4 * q4] = vb.x; wb[4 * q4 + 1] = vb.y; wb[4 * q4 + 2] = vb.z; wb[4 * q4 + 3] = vb.w;
+      }
+    } else if constexpr (RP == 16) {
       const uint4 va = rowA0 < m ? __ldg(reinterpret_cast<const uint4 *>(xs + rowA0)) : make_uint4(0, 0, 0, 0);
       const uint4 vb = rowB0 < m ? __ldg(reinterpret_cast<const uint4 *>(xs + rowB0)) : make_uint4(0, 0, 0, 0);
       wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
@@ -315,9 +323,16 @@ __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_kernel(const FillArg
     const StripTask task = a.tasks[t];
     const PairDesc P = a.pairs[task.pair];
     const int s = (int)task.strip;
-    // main launch: strip pairs of 64*16 = 1024 rows; a pair's 512-row last strip pair (see
-    // strip_geometry) runs in the second launch with 8 rows per half lane
-    const int row_base = (P.half_last && s == P.nstrips - 1) ? (int)P.mpad - 64 * RP : s * (64 * RP);
+    // main launch: strip pairs of 64 * main_rp rows (1024 or 2048); a pair's shorter last strip
+    // pairs (1024 rows in the three-level geometry, then 512 rows; see strip_geometry) run in later
+    // launches with 16 / 8 rows per half lane
+    int row_base;
+    if (RP == a.main_rp)
+      row_base = s * (64 * RP);
+    else if (RP == 16)
+      row_base = main_strips(P.nstrips, P.half_last) * 2048;
+    else
+      row_base = (int)P.mpad - 512;
     process_strip_pair<RP>(a, P, s, row_base, lane, s_sel[warp], s_top[warp]);
   }
 }
@@ -347,6 +362,8 @@ __global__ void build_sel16_kernel(const uint8_t *__restrict__ codes, uint8_t *_
 
 typedef void (*Fill16Ptr)(const FillArgs);
 Fill16Ptr pick16(int rp, int minb) {
+  // 32 rows per half lane: 128 registers without spills = 4 CTAs per SM (cfg4 fill 4.14 s; 3 CTAs: 4.20 s)
+  if (rp == 32) return minb == 3 ? fill16_kernel<32, 3> : fill16_kernel<32, 4>;
   if (rp == 16) {
     // 6 CTAs per SM (<= 80 registers): 161 ms per cfg3 job against 168 (5 CTAs), 173 (4), 180 (7)
     if (minb == 4) return fill16_kernel<16, 4>;
@@ -362,13 +379,13 @@ Fill16Ptr pick16(int rp, int minb) {
 
 // 16-bit relative scores need: byte-sized gains, and the spread of a strip pair plus the growth
 // over one re-base interval below 2^16.  Returns the re-base interval's log2 (>= 6), or 0.
-int fill16_rebase_shift(int pxy, int pgap) {
+int fill16_rebase_shift(int pxy, int pgap, int rp) {
   if (pxy < 0 || pgap < 0 || 2 * (int64_t)pgap > 127) return 0;
   if (pgap == 0) return 10;
-  // values within 2*pgap*(256 + 64*16) of each other + 2*pgap*4 per step + 1024 steps of slack for halves
+  // values within 2*pgap*(256 + 64*rp) of each other + 2*pgap*4 per step + 1024 steps of slack for halves
   // that have finished
   for (int ks = 10; ks >= 6; --ks)
-    if (2ll * pgap * (4ll * (1 << ks) + 256 + 64 * 16 + 4 * 256) <= 65535 - 2ll * pgap) return ks;
+    if (2ll * pgap * (4ll * (1 << ks) + 256 + 64 * rp + 4 * 256) <= 65535 - 2ll * pgap) return ks;
   return 0;
 }
 

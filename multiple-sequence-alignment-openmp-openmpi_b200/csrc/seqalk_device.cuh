@@ -57,6 +57,8 @@ __host__ __device__ inline int num_strips(int m, int R) { return (m + strip_rows
 // Strip geometry of a pair: all strips have 32*R rows, except that with `mixed` (tile mode,
 // R = 32) a last strip covering <= 512 remaining rows is a half strip of 16 rows per lane —
 // halves the average row padding (5.0 % -> 2.5 % of the cells on BASELINE config 4).
+// `half_last` is a tail code: bit 0 = the pair ends with a 512-row strip, bit 1 = (three-level
+// geometry only) a 1024-row strip before that / at the end.
 struct StripGeom {
   int nstrips;
   uint32_t mpad;
@@ -71,6 +73,25 @@ __host__ __device__ inline StripGeom strip_geometry(int m, int R, bool mixed) {
   g.mpad = (uint32_t)((g.nstrips - 1) * h + (g.half_last ? h / 2 : h));
   return g;
 }
+// Three-level geometry of the packed fill with 32 rows per half lane: strip pairs of 2048 rows,
+// then at most one of 1024 and one of 512 rows, so that the padding stays <= 512 rows.
+__host__ __device__ inline StripGeom strip_geometry3(int m) {
+  StripGeom g;
+  int n0 = m / 2048;
+  const int rem = m - n0 * 2048;
+  uint32_t tail = 0;
+  if (rem == 0) tail = 0;
+  else if (rem <= 512) tail = 1;
+  else if (rem <= 1024) tail = 2;
+  else if (rem <= 1536) tail = 3;
+  else ++n0;
+  g.nstrips = n0 + (int)(tail & 1) + (int)(tail >> 1);
+  g.mpad = (uint32_t)(n0 * 2048 + ((tail & 2) ? 1024 : 0) + ((tail & 1) ? 512 : 0));
+  g.half_last = tail;
+  return g;
+}
+// strips of the main height in a pair with tail code `tail`
+__host__ __device__ inline int main_strips(int nstrips, uint32_t tail) { return nstrips - (int)(tail & 1) - (int)((tail >> 1) & 1); }
 
 // Direction codes.  16 cells per 32-bit word, shifted in MSB-first in the order
 // idx = c*R + r (column-major inside the lane's R x 4 block).

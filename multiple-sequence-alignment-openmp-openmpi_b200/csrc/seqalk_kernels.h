@@ -54,6 +54,7 @@ struct FillArgs {
   // 16x2-packed fill (fill16.cu) only:
   const uint8_t *sel16;     // selector streams, one per sequence, at byte offset 2 * (offset of the sequence)
   int32_t rebase_shift;     // log2 of the re-base interval in macro steps
+  int32_t main_rp;          // rows per half lane of the job's main strip pairs (16: 1024-row, 32: 2048-row strip pairs)
 };
 
 struct TracebackArgs {
@@ -74,6 +75,7 @@ struct TracebackArgs {
   int32_t R;                // rows per lane the fill used (direction layout)
   int32_t ck16;             // tile mode: 0 = int32 column checkpoints (fill.cu); else the 16x2-packed fill's
                             // checkpoints (fill16.cu), value = log2 of its re-base interval
+  int32_t main_rows;        // packed checkpoints: rows of the job's main strip pairs (1024 or 2048)
   int32_t strip_scan;       // 1: the input contains '_' (the gap character): apply the reference's
                             // strip rule literally (submit/xuliny-seqalkway.cpp:191-202): the alignment
                             // starts after the LAST column holding '_' in both strings
@@ -123,7 +125,7 @@ cudaError_t launch_fill(const FillArgs &args, const FillVariant &v, int sm_count
 // 16x2-packed score-only fill: rp = rows per half lane (16: strip pairs of 1024 rows, 8: 512 rows)
 cudaError_t launch_fill16(const FillArgs &args, int rp, int minb, int sm_count, cudaStream_t stream);
 int fill16_blocks_per_sm(int rp, int minb);
-int fill16_rebase_shift(int pxy, int pgap);  // 0: penalties do not fit the 16-bit scheme
+int fill16_rebase_shift(int pxy, int pgap, int rp);  // 0: penalties do not fit the 16-bit scheme with rp rows per half lane
 cudaError_t launch_build_sel16(const uint8_t *codes, uint8_t *sel16, const uint32_t *off_dev, const int32_t *len_dev,
                                int k, int maxlen, cudaStream_t stream);
 // entries of a strip pair's base log for a pair with nq macro columns

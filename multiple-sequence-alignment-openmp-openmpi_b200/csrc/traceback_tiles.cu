@@ -41,7 +41,7 @@ struct TileCtx {
   const int32_t *brow, *ck;    // kept rows, column checkpoints
   // 16x2-packed column checkpoints (fill16.cu), ck16 = log2 of the fill's re-base interval (0: int32
   // checkpoints): image (k, half) of mpad/2 packed words, relative to the base the fill logged
-  int ck16;
+  int ck16, main_rows;
   int nstrips, half_last;
 };
 
@@ -63,6 +63,7 @@ __device__ __forceinline__ TileCtx make_ctx(const TracebackArgs &a, const PairDe
   T.brow = a.brow + P.brow_off;
   T.ck = reinterpret_cast<const int32_t *>(a.dirs + P.dir_off);
   T.ck16 = a.ck16;
+  T.main_rows = a.main_rows;
   T.nstrips = P.nstrips;
   T.half_last = (int)P.half_last;
   return T;
@@ -101,15 +102,28 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
     }
     if (cb > 0 && T.ck16) {
       // left edge from the packed fill's checkpoint cb-1.  Row r0 lies in the strip pair starting
-      // at row sp0 (1024 rows; the pair's last one 512 rows if half_last), in its first half A (low
+      // at row sp0, in its first half A (low
       // 16 bits) or second half B (high 16 bits), on virtual lane vl of 64; that lane reached the
       // checkpoint column (macro column 64*cb - 1) at macro step 64*cb - 1 + vl: the base logged
       // for that step makes the value absolute:  H' = -(base + relative).
-      const int tail0 = (int)T.mpad - 512;
-      const bool in_half = T.half_last && r0 >= tail0;
-      const int sp_rows = in_half ? 512 : 1024;
-      const int s = in_half ? T.nstrips - 1 : r0 >> 10;
-      const int sp0 = in_half ? tail0 : (r0 >> 10) << 10;
+      // (main strip pairs of main_rows rows; then, by the tail code, one of 1024 rows (three-level
+      // geometry) and / or one of 512 rows)
+      const int nmain = main_strips(T.nstrips, (uint32_t)T.half_last);
+      const int main_end = nmain * T.main_rows;
+      int sp_rows, s, sp0;
+      if (r0 < main_end) {
+        sp_rows = T.main_rows;
+        s = r0 / T.main_rows;
+        sp0 = s * T.main_rows;
+      } else if ((T.half_last & 2) && r0 < main_end + 1024) {
+        sp_rows = 1024;
+        s = nmain;
+        sp0 = main_end;
+      } else {
+        sp_rows = 512;
+        s = T.nstrips - 1;
+        sp0 = (int)T.mpad - 512;
+      }
       const int rem = r0 - sp0;
       const int half = rem >= (sp_rows >> 1) ? 1 : 0;
       const int vl = rem / (sp_rows >> 6);
