@@ -303,7 +303,7 @@ def main():
         T = len(genes) * (len(genes) - 1) // 2
         # chunks of task ids: rank 0 folds the hash chain of chunk c while the GPUs work on chunk c+1
         # (chunks of >= 32k tasks: smaller ones only add kernel tails)
-        nchunks = args.nchunks or max(1, min(9, T // 32768))
+        nchunks = args.nchunks or max(1, min(14, T // 16384))
         plan = dmod.ShardPlan(lens, world, nchunks)
         shard = dmod.GpuShard(genes, pxy, pgap, plan, rank, local_rank)
         result = None

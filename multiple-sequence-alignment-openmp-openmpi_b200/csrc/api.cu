@@ -10,6 +10,7 @@
 #include <stdexcept>
 #include <string>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <thread>
 #include <vector>
@@ -154,25 +155,37 @@ struct DeviceArray {
   }
 };
 
-// Chunk c covers task ids [bounds[c], bounds[c+1]).  The host folds chunk c (about 0.75 us per task,
+// Chunk c covers task ids [bounds[c], bounds[c+1]).  The host folds chunk c (0.6 - 0.8 us per task,
 // serial by construction) while the GPUs work on the chunks after it; what stays exposed at the end
-// is  max over c of  fold(chunks >= c) - gpu(chunks > c).  Equal chunks leave the whole last
-// chunk's fold exposed; with >= 5 chunks (and >= 4096 tasks) the last three hold 8 %, 5 % and 3 % of
-// the tasks, which keeps the backlog below the last chunk's own fold up to 8 GPUs (the GPUs then
-// need about 1.3 us per task).  With 4 chunks: a 4 % last chunk.
+// is  max over c of  fold(chunks >= c) - gpu(chunks > c).
+// With the two overlapped batch pipelines of a GPU (engine.cu) chunks complete in PAIRS: the
+// traceback of chunk 2p only gets SMs when the persistent fill of chunk 2p+1 winds down (8-GPU
+// trace, profiles/r02_n8_chunk_trace.txt: chunks 4 and 5 — 28 % of the tasks — arrived together
+// 140 ms before the end and left 33 ms of fold exposed).  So the schedule is laid out in pairs of
+// equal chunks: body pairs of equal size, then up to four pairs shrinking by 0.6 each — the fold
+// of one pair (0.8 us per task) fits into the GPU time of the next one (>= 1.3 us per task up to
+// 8 GPUs) — so that the exposed part is the fold of the last, smallest pair.
 void chunk_bounds(int64_t T, int nchunks, std::vector<int64_t> &b) {
   b.assign((size_t)nchunks + 1, 0);
-  if (nchunks >= 5 && T >= 4096) {
-    const int body = nchunks - 3;
-    const int64_t t3 = T * 3 / 100, t5 = T * 5 / 100, t8 = T * 8 / 100;
-    const int64_t body_total = T - t3 - t5 - t8;
-    for (int c = 0; c <= body; ++c) b[c] = body_total * c / body;
-    b[body + 1] = body_total + t8;
-    b[body + 2] = body_total + t8 + t5;
-  } else if (nchunks >= 4 && T >= 4096) {
-    const int body = nchunks - 1;
-    const int64_t body_total = T - T * 4 / 100;
-    for (int c = 0; c <= body; ++c) b[c] = body_total * c / body;
+  if (nchunks >= 4 && T >= 4096) {
+    const int npairs = (nchunks + 1) / 2;  // the last pair is a single chunk when nchunks is odd
+    const int ntaper = std::min(4, npairs - 1);
+    std::vector<double> w((size_t)nchunks);
+    double sum = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int p = c / 2;
+      const int k = p - (npairs - ntaper - 1);  // 0 for body pairs, 1.. for the tapered ones
+      double pw = 1.0;
+      for (int i = 0; i < k; ++i) pw *= 0.6;
+      const int in_pair = (2 * p + 1 < nchunks) ? 2 : 1;
+      w[(size_t)c] = pw / in_pair;
+      sum += w[(size_t)c];
+    }
+    double acc = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      acc += w[(size_t)c];
+      b[(size_t)c + 1] = std::max(b[(size_t)c], (int64_t)((double)T * (acc / sum)));
+    }
   } else {
     for (int c = 0; c <= nchunks; ++c) b[c] = T * c / nchunks;
   }
@@ -207,7 +220,7 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
                     char digest_hex[129]) {
   const int N = (int)r.workers.size();
   const int64_t T = (int64_t)k * (k - 1) / 2;
-  int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(9, T / 32768));
+  int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(14, T / 16384));
   if (const char *e = std::getenv("SEQALK_PEER_CHUNKS"))  // tests: force several chunks on small jobs
     nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(64, T), std::atoi(e)));
   // SEQALK_TRACE=1: phase times of this call on stderr
@@ -282,30 +295,53 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
   std::vector<uint8_t> digests((size_t)T * 64);
   size_t hl = 0;
   digest_hex[0] = 0;
-  std::thread folder;
+  // one folder thread takes the chunks in order as their results reach the host, so that this
+  // thread never waits for a fold and sees every chunk the moment the GPUs finish it
+  std::mutex fmu;
+  std::condition_variable fcv;
+  int ready = 0;      // chunks copied to the host
+  bool stop = false;  // no more chunks will come
+  std::thread folder([&]() {
+    for (int c = 0;; ++c) {
+      {
+        std::unique_lock<std::mutex> g(fmu);
+        fcv.wait(g, [&] { return ready > c || stop; });
+        if (ready <= c) return;
+      }
+      const size_t lo = (size_t)bounds[c], n = (size_t)(bounds[c + 1] - bounds[c]);
+      if (n) fold_chain(digests.data() + 64 * lo, n, digest_hex, &hl);
+      if (trace) mark("folded chunk", c);
+    }
+  });
   std::string error;
   try {
     for (int c = 0; c < nchunks; ++c) {
-      for (int d = 0; d < N; ++d) {
-        r.workers[d]->wait_chunk((size_t)c, nullptr);
-        mark("chunk done on GPU", d);
-      }
+      for (int d = 0; d < N; ++d) r.workers[d]->wait_chunk((size_t)c, nullptr);
+      mark("chunk done on every GPU", c);
       if (c == nchunks - 1) r.prof[2] = ms_since(t_start);  // every GPU has finished its last chunk
       const size_t lo = (size_t)bounds[c], n = (size_t)(bounds[c + 1] - bounds[c]);
-      if (!n) continue;
-      const auto t_copy = std::chrono::steady_clock::now();
-      SEQALK_CUDA(cudaSetDevice(0));
-      SEQALK_CUDA(cudaMemcpy(penalties + lo, pen0 + lo, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-      SEQALK_CUDA(cudaMemcpy(digests.data() + 64 * lo, dig0 + 64 * lo, n * 64, cudaMemcpyDeviceToHost));
-      r.prof[4] += ms_since(t_copy);
-      if (folder.joinable()) folder.join();
-      mark("folding chunk", c);
-      folder = std::thread([&, lo, n]() { fold_chain(digests.data() + 64 * lo, n, digest_hex, &hl); });
+      if (n) {
+        const auto t_copy = std::chrono::steady_clock::now();
+        SEQALK_CUDA(cudaSetDevice(0));
+        SEQALK_CUDA(cudaMemcpy(penalties + lo, pen0 + lo, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        SEQALK_CUDA(cudaMemcpy(digests.data() + 64 * lo, dig0 + 64 * lo, n * 64, cudaMemcpyDeviceToHost));
+        r.prof[4] += ms_since(t_copy);
+      }
+      {
+        std::lock_guard<std::mutex> g(fmu);
+        ready = c + 1;
+      }
+      fcv.notify_one();
     }
   } catch (const std::exception &e) {
     error = e.what();
   }
-  if (folder.joinable()) folder.join();
+  {
+    std::lock_guard<std::mutex> g(fmu);
+    stop = true;
+  }
+  fcv.notify_one();
+  folder.join();
   mark("folded");
   r.prof[3] = ms_since(t_start) - r.prof[2];  // fold (and last copy) left exposed after the GPUs finished
   for (int d = 0; d < N; ++d) {

@@ -27,6 +27,7 @@ fails loudly without one.
 """
 from __future__ import annotations
 
+import queue
 import threading
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -180,41 +181,59 @@ def run_sharded(plan: ShardPlan, rank: int, run_chunk: Callable[[int], "object"]
     world = plan.world
     penalties = np.zeros(plan.T, dtype=np.int32) if rank == 0 else None
     digests = np.zeros((plan.T, 64), dtype=np.uint8) if rank == 0 else None
-    state = {"hex": ""}
+    state = {"hex": "", "error": None}
+    # rank 0: one folder thread takes the gathered chunks in order, so that the loop below never
+    # waits for a fold (the chunks of a GPU complete in pairs, see chunk_bounds in csrc/api.cu)
+    todo: "queue.Queue" = queue.Queue()
+
+    def fold_loop():
+        while True:
+            item = todo.get()
+            if item is None:
+                return
+            c, host = item
+            try:
+                _scatter(plan, c, host, penalties, digests)
+                b, e = plan.bounds[c], plan.bounds[c + 1]
+                state["hex"] = fold_chain(digests[b:e], state["hex"])
+            except Exception as exc:  # surfaced after the loop
+                state["error"] = exc
+                return
+
     folder: Optional[threading.Thread] = None
-
-    def fold_range(c: int, host: np.ndarray):
-        _scatter(plan, c, host, penalties, digests)
-        b, e = plan.bounds[c], plan.bounds[c + 1]
-        state["hex"] = fold_chain(digests[b:e], state["hex"])
-
-    for c in range(plan.nchunks):
-        send = run_chunk(c)
-        host = None
-        if world > 1 and send.device.type == "cpu" and dist.get_backend(group) != "gloo":
-            # host gather: the records are already in host memory on every rank
-            hg = host_group(group)
-            parts = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
-            dist.gather(send, parts, dst=dist.get_global_rank(hg, 0), group=hg)
-            if rank == 0:
-                host = np.stack([p.numpy() for p in parts])
-        elif world > 1:
-            rows = send.shape[0]
-            flat = torch.empty((world * rows, send.shape[1]), dtype=send.dtype, device=send.device)
-            dist.all_gather_into_tensor(flat, send.contiguous(), group=group)
-            recv = flat.view(world, rows, send.shape[1])
-            if rank == 0:
-                host = recv.cpu().numpy()  # D2H of the gathered records (synchronises the stream)
-        elif rank == 0:
-            host = send.unsqueeze(0).cpu().numpy()
-        if rank == 0:
-            if folder is not None:
-                folder.join()
-            folder = threading.Thread(target=fold_range, args=(c, host))
-            folder.start()
-    if folder is not None:
-        folder.join()
     if rank == 0:
+        folder = threading.Thread(target=fold_loop)
+        folder.start()
+
+    try:
+        for c in range(plan.nchunks):
+            send = run_chunk(c)
+            host = None
+            if world > 1 and send.device.type == "cpu" and dist.get_backend(group) != "gloo":
+                # host gather: the records are already in host memory on every rank
+                hg = host_group(group)
+                parts = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+                dist.gather(send, parts, dst=dist.get_global_rank(hg, 0), group=hg)
+                if rank == 0:
+                    host = np.stack([p.numpy() for p in parts])
+            elif world > 1:
+                rows = send.shape[0]
+                flat = torch.empty((world * rows, send.shape[1]), dtype=send.dtype, device=send.device)
+                dist.all_gather_into_tensor(flat, send.contiguous(), group=group)
+                recv = flat.view(world, rows, send.shape[1])
+                if rank == 0:
+                    host = recv.cpu().numpy()  # D2H of the gathered records (synchronises the stream)
+            elif rank == 0:
+                host = send.unsqueeze(0).cpu().numpy()
+            if rank == 0:
+                todo.put((c, host))
+    finally:
+        if folder is not None:
+            todo.put(None)
+            folder.join()
+    if rank == 0:
+        if state["error"] is not None:
+            raise state["error"]
         return state["hex"], penalties
     return None
 
