@@ -691,15 +691,31 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       strip0 += (uint32_t)d.nstrips;
       max_strips = std::max(max_strips, d.nstrips);
     }
-    // strip queue ordered (strip, pair): a strip's predecessor is always claimed earlier.
+    // strip queue: a strip's predecessor is always claimed earlier (no deadlock without a
+    // cooperative launch).  Default order = critical path first (big13 fill 46.0 -> 44.5 ms, no
+    // difference on many-pair jobs).
     // Shorter last strips (tile mode) go to the end: they run in later launches (1024-row strip
     // pairs of the three-level geometry with 16 rows per half lane, then the 512-row ones), after
     // all their predecessors have finished.
     size_t n_main = 0, n_mid = 0, n_half = 0;
     {
-      for (int s = 0; s < max_strips; ++s)
-        for (size_t p = 0; p < B.count; ++p)
-          if (s < main_strips(hp[p].nstrips, hp[p].half_last)) ht[n_main++] = StripTask{(uint32_t)p, (uint32_t)s};
+      static const bool by_remaining = [] {
+        const char *e = std::getenv("SEQALK_QUEUE_REMAINING");  // 0: plain (strip, pair) order
+        return !e || std::atoi(e) != 0;
+      }();
+      if (by_remaining) {
+        // critical path first: strips ordered by the number of main strips still to come in their
+        // pair (a predecessor has more of them, so it is still claimed earlier)
+        for (int r = max_strips; r >= 1; --r)
+          for (size_t p = 0; p < B.count; ++p) {
+            const int ms = main_strips(hp[p].nstrips, hp[p].half_last);
+            if (ms >= r) ht[n_main++] = StripTask{(uint32_t)p, (uint32_t)(ms - r)};
+          }
+      } else {
+        for (int s = 0; s < max_strips; ++s)
+          for (size_t p = 0; p < B.count; ++p)
+            if (s < main_strips(hp[p].nstrips, hp[p].half_last)) ht[n_main++] = StripTask{(uint32_t)p, (uint32_t)s};
+      }
       for (size_t p = 0; p < B.count; ++p)
         if (hp[p].half_last & 2)
           ht[n_main + n_mid++] = StripTask{(uint32_t)p, (uint32_t)main_strips(hp[p].nstrips, hp[p].half_last)};
@@ -794,6 +810,8 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.long_pairs = few_pairs_ ? 1 : 0;
     ta.strip_scan = strip_scan_ ? 1 : 0;
     if (const char *e = std::getenv("SEQALK_TB_LONG")) ta.long_pairs = std::atoi(e) ? 1 : 0;
+    ta.half_warp = 0;  // measured slower at 256-column tiles (11 instead of 23 warps per SM), profiles/experiments
+    if (const char *e = std::getenv("SEQALK_TB_HALF")) ta.half_warp = std::atoi(e) ? 1 : 0;
     if (!fill_only) SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));
 

@@ -64,6 +64,7 @@ struct TracebackArgs {
   int32_t mode;             // tile mode: MODE_* of the recompute (same arithmetic as the fill)
   int32_t addmode;          // tile mode: 2 = IDP.4A cost lookup in the recompute
   int32_t long_pairs;       // tile mode: 1 = four warps per pair (walk + look-ahead recompute)
+  int32_t half_warp;        // tile mode, many pairs: 1 = two pairs per warp (16 lanes x 8 rows per tile)
   const PairDesc *pairs;
   uint32_t npairs;
   const uint8_t *dirs;

@@ -16,9 +16,12 @@ namespace seqalk {
 
 namespace {
 
-constexpr int RT = TILE_ROWS / 32;  // rows per lane in the recompute: 32 lanes x RT rows = TILE_ROWS
-constexpr int WPE = RT / 4;         // 32-bit words of direction codes per lane and macro column
-static_assert(RT == 8 || RT == 4, "tile height");
+// A tile is recomputed by a group of LN = TILE_ROWS / RT lanes owning RT rows each: the whole warp
+// (RT = TILE_ROWS / 32: the four-warp kernel of long pairs) or half a warp (RT = TILE_ROWS / 16:
+// the many-pair kernel, two pairs per warp — half the wavefront ramp per tile).
+constexpr int RT_WARP = TILE_ROWS / 32;
+constexpr int RT_HALF = TILE_ROWS / 16;
+static_assert(RT_WARP == 4 && RT_HALF == 8, "tile height 128: 4 rows per lane (warp) / 8 rows per lane (half warp)");
 
 // Right-to-left output of the two alignment strings.  Every lane of the walking warp carries
 // the same position; the characters of 32 consecutive steps are stored by 32 lanes at once.
@@ -71,7 +74,7 @@ __device__ __forceinline__ TileCtx make_ctx(const TracebackArgs &a, const PairDe
 
 // Shared-memory image of one tile: direction codes [CKQ][32] + the tile's characters, and
 // (STAGE) the tile's top edge: per macro column the 4 values of the kept row + the y word.
-constexpr int TILE_DIR_BYTES = CKQ * 32 * 4 * WPE;
+constexpr int TILE_DIR_BYTES = CKQ * TILE_ROWS;  // 2 bits per cell of a TILE_ROWS x 4*CKQ tile
 constexpr int TILE_CHAR_BYTES = TILE_ROWS + 4 * CKQ;
 constexpr int TILE_EDGE_BYTES = CKQ * 20;
 constexpr int tile_smem_bytes(bool stage) { return TILE_DIR_BYTES + TILE_CHAR_BYTES + (stage ? TILE_EDGE_BYTES : 0); }
@@ -80,14 +83,20 @@ constexpr int tile_smem_bytes(bool stage) { return TILE_DIR_BYTES + TILE_CHAR_BY
 #endif
 
 // Recomputes the directions of tile (hs, cb), macro columns [0, tq) and lanes [0, tmax], into
-// `tile` (one warp).  Same sweep as the fill: lane t owns RT rows, trails lane t-1 by one macro
-// column; left edge = column checkpoint cb-1, top edge = kept row hs-1.
-// STAGE: the warp first copies the top edge to shared memory with a few wide loads; otherwise
+// `tile`, by a group of LN = TILE_ROWS / RT lanes (`lane` = index inside the group; every lane of
+// the WARP must call this together, with the same `nsteps` >= tq + tmax: the groups of a warp run
+// the step loop in lockstep, each on its own tile).  Same sweep as the fill: lane t owns RT rows,
+// trails lane t-1 by one macro column; left edge = column checkpoint cb-1, top edge = kept row hs-1.
+// tq = 0: nothing to do for this group (it only keeps the others company).
+// STAGE: the group first copies the top edge to shared memory with a few wide loads; otherwise
 // lane 0 fetches it from global memory one macro column ahead, which exposes the load latency on
 // every step unless other warps cover it.
-template <int MODE, int ADDMODE, bool STAGE>
-__device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb, int tq, int tmax, uint8_t *tile,
-                                               int lane) {
+template <int MODE, int ADDMODE, bool STAGE, int RT>
+__device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb, int tq, int tmax, int nsteps,
+                                               uint8_t *tile, int lane) {
+  constexpr int LN = TILE_ROWS / RT;  // lanes per tile
+  constexpr int WPE = RT / 4;         // 32-bit words of direction codes per lane and macro column
+  static_assert(RT == 8 || RT == 4, "rows per lane");
   const unsigned FULL = 0xffffffffu;
   uint32_t *sdirs = reinterpret_cast<uint32_t *>(tile);
   const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ, q0 = cb * CKQ;
@@ -152,24 +161,22 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
       for (int r = 0; r < RT; ++r) h[r] = 0;
     }
   }
-  {  // stage the tile's characters (rows / columns past the ends are never walked)
-    static_assert(CKQ == 64 || CKQ == 32, "8 or 4 y characters per lane");
-    const int r0 = row0 + lane * RT, c0 = col0 + lane * (CKQ / 8);
+  if (tq > 0) {  // stage the tile's characters (rows / columns past the ends are never walked)
+    const int r0 = row0 + lane * RT;
     if (RT == 8)
       reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES)[lane] =
           r0 < T.m ? *reinterpret_cast<const uint64_t *>(T.xs + r0) : 0ull;
     else
       reinterpret_cast<uint32_t *>(tile + TILE_DIR_BYTES)[lane] =
           r0 < T.m ? *reinterpret_cast<const uint32_t *>(T.xs + r0) : 0u;
-    if (CKQ == 64)
-      reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES + TILE_ROWS)[lane] =
-          c0 < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + c0) : 0ull;
-    else
-      reinterpret_cast<uint32_t *>(tile + TILE_DIR_BYTES + TILE_ROWS)[lane] =
-          c0 < T.n ? *reinterpret_cast<const uint32_t *>(T.ys + c0) : 0u;
+    static_assert((4 * CKQ) % (8 * LN) == 0, "8 y characters per lane and round");
+#pragma unroll
+    for (int c = lane * 8; c < 4 * CKQ; c += 8 * LN)
+      *reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES + TILE_ROWS + c) =
+          col0 + c < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + col0 + c) : 0ull;
   }
   const int32_t *toprow = hs > 0 ? T.brow + (uint64_t)(hs - 1) * T.bstride : nullptr;
-  int dg = __shfl_up_sync(FULL, h[RT - 1], 1);
+  int dg = __shfl_up_sync(FULL, h[RT - 1], 1, LN);
   if (lane == 0) dg = (toprow && cb > 0) ? __ldcg(toprow + col0 - 1) : 0;
   int outv[4] = {0, 0, 0, 0};
   unsigned yw = 0;
@@ -179,25 +186,24 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
   int4 *stop = reinterpret_cast<int4 *>(tile + TILE_DIR_BYTES + TILE_CHAR_BYTES);
   unsigned *sy = reinterpret_cast<unsigned *>(stop + CKQ);
   if (STAGE) {
-    for (int q = lane; q < tq; q += 32) {
+    for (int q = lane; q < tq; q += LN) {
       stop[q] = top4 ? __ldcg(top4 + q) : make_int4(0, 0, 0, 0);
       sy[q] = __ldg(T.yw32 + q0 + q);
     }
     __syncwarp();
-  } else if (lane == 0) {
+  } else if (lane == 0 && tq > 0) {
     ynext = __ldg(T.yw32 + q0);
     if (top4) top = __ldcg(top4);
   }
-  const int nsteps = tq + tmax;
   for (int q = 0; q < nsteps; ++q) {
     int up_in[4];
-    up_in[0] = __shfl_up_sync(FULL, outv[0], 1);
-    up_in[1] = __shfl_up_sync(FULL, outv[1], 1);
-    up_in[2] = __shfl_up_sync(FULL, outv[2], 1);
-    up_in[3] = __shfl_up_sync(FULL, outv[3], 1);
-    unsigned ny = __shfl_up_sync(FULL, yw, 1);
+    up_in[0] = __shfl_up_sync(FULL, outv[0], 1, LN);
+    up_in[1] = __shfl_up_sync(FULL, outv[1], 1, LN);
+    up_in[2] = __shfl_up_sync(FULL, outv[2], 1, LN);
+    up_in[3] = __shfl_up_sync(FULL, outv[3], 1, LN);
+    unsigned ny = __shfl_up_sync(FULL, yw, 1, LN);
     if (STAGE) {
-      const int qs = min(q, tq - 1);  // broadcast reads; only lane 0 uses them, and only while q < tq
+      const int qs = max(min(q, tq - 1), 0);  // broadcast reads; only lane 0 uses them, and only while q < tq
       top = stop[qs];
       ynext = sy[qs];
     }
@@ -215,9 +221,9 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
       unsigned bits[RT / 4];
       macro_step<RT, MODE, ADDMODE, true>(h, dg, xc, up_in, yw, T.A, T.B, 1, -1, outv, bits);
       if (RT == 8)
-        reinterpret_cast<uint2 *>(sdirs)[qc * 32 + lane] = make_uint2(bits[0], bits[WPE - 1]);
+        reinterpret_cast<uint2 *>(sdirs)[qc * LN + lane] = make_uint2(bits[0], bits[WPE - 1]);
       else
-        sdirs[qc * 32 + lane] = bits[0];
+        sdirs[qc * LN + lane] = bits[0];
     }
   }
 }
@@ -246,13 +252,16 @@ __device__ __forceinline__ void emit_steps(const uint8_t *sxb, const uint8_t *sy
 }
 
 // Walks the path inside a recomputed tile from (i, j) until it leaves through the top or the
-// left edge.  Every lane follows the walk.  One shared-memory word holds the 16 codes of an
+// left edge.  Every lane of the group (`lane` = index inside it, at least 16 lanes) follows the walk.  One shared-memory word holds the 16 codes of an
 // RT x (16 / RT) block of cells; while the path stays inside the block the word is kept rotated
 // so that the current cell's code sits in the top two bits (a step is: read the code, rotate by
 // a table look-up, move, append the code to the history).  The history is emitted by up to 15
 // lanes at once (emit_steps).
+template <int RT>
 __device__ __forceinline__ void walk_tile(const uint8_t *tile, int row0, int col0, int &i, int &j, PathOut &W,
                                           int pxy, int pgap, int lane) {
+  constexpr int LN = TILE_ROWS / RT;  // lanes that recomputed the tile (layout of the code words)
+  constexpr int WPE = RT / 4;
   constexpr int CW = 16 / RT;         // columns of a word's block
   constexpr int MAXB = RT + CW - 1;   // most steps inside one block
   // rotate amounts (2 bits per cell, cell index = column * RT + row) by code
@@ -272,7 +281,7 @@ __device__ __forceinline__ void walk_tile(const uint8_t *tile, int row0, int col
     }
     const int bl = li & ~(RT - 1), bj = lj & ~(CW - 1);
     const unsigned idx = (unsigned)(lj & (CW - 1)) * RT + (unsigned)(li & (RT - 1));
-    const uint32_t word = sdirs32[(((unsigned)lj >> 2) * 32 + (unsigned)li / RT) * WPE + ((unsigned)(lj & 3) / CW)];
+    const uint32_t word = sdirs32[(((unsigned)lj >> 2) * LN + (unsigned)li / RT) * WPE + ((unsigned)(lj & 3) / CW)];
     uint32_t w = __funnelshift_l(word, word, 2 * idx);
 #pragma unroll 2
     do {
@@ -288,15 +297,17 @@ __device__ __forceinline__ void walk_tile(const uint8_t *tile, int row0, int col
   j = col0 + lj + 1;
 }
 
-// Tails (only one of i, j is non-zero) and the per-pair result record (one warp).
+// Tails (only one of i, j is non-zero) and the per-pair result record, by a group of LN lanes
+// (`lane` = index inside the group, `gmask` = the group's lanes in the warp, `g0` = its first lane).
+template <int LN>
 __device__ __forceinline__ void finish_pair(const TracebackArgs &a, const TileCtx &T, uint32_t p, int i, int j,
-                                            PathOut &W, int lane) {
-  for (int t = lane; t < i; t += 32) {
+                                            PathOut &W, int lane, unsigned gmask, int g0) {
+  for (int t = lane; t < i; t += LN) {
     W.o1[W.pos - 1 - t] = T.xs[i - 1 - t];
     W.o2[W.pos - 1 - t] = '_';
   }
   W.pos -= i;
-  for (int t = lane; t < j; t += 32) {
+  for (int t = lane; t < j; t += LN) {
     W.o1[W.pos - 1 - t] = '_';
     W.o2[W.pos - 1 - t] = T.ys[j - 1 - t];
   }
@@ -304,20 +315,20 @@ __device__ __forceinline__ void finish_pair(const TracebackArgs &a, const TileCt
   if (a.strip_scan) {
     // '_' inside the inputs: the reference strips everything up to the LAST column that holds
     // '_' in both strings (submit/xuliny-seqalkway.cpp:191-202), not only the leading pad
-    __syncwarp();
+    __syncwarp(gmask);
     const int L = T.m + T.n;
     int found = -1;
-    for (int base = L - 32; base + 31 >= W.pos && found < 0; base -= 32) {
+    for (int base = L - LN; base + LN - 1 >= W.pos && found < 0; base -= LN) {
       const int idx = base + lane;
       const bool hit = idx >= W.pos && idx < L && W.o1[idx] == '_' && W.o2[idx] == '_';
-      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      const unsigned b = __ballot_sync(gmask, hit) >> g0;
       if (b) found = base + 31 - __clz(b);
     }
     if (found >= 0) W.pos = found + 1;
   }
   int cost = W.cost;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, d);
+  for (int d = LN / 2; d > 0; d >>= 1) cost += __shfl_xor_sync(gmask, cost, d);
   if (lane == 0) {
     PairAlign res;
     res.start = (uint32_t)W.pos;
@@ -327,10 +338,11 @@ __device__ __forceinline__ void finish_pair(const TracebackArgs &a, const TileCt
   }
 }
 
-// One warp per pair (jobs with many pairs): recompute the part of the tile up-left of the entry
-// cell, walk it, repeat.
+// One warp per pair: recompute the part of the tile up-left of the entry cell, walk it, repeat.
+// (SEQALK_TB_HALF=0; the default for jobs with many pairs is the half-warp kernel below.)
 template <int MODE, int ADDMODE, bool STAGE>
 __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs a) {
+  constexpr int RT = RT_WARP;
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x;
   const uint32_t p = blockIdx.x;
@@ -343,12 +355,51 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
     const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ;
     const int tq = ((j - 1 - col0) >> 2) + 1;  // macro columns needed
     const int tmax = (i - 1 - row0) / RT;      // last lane needed
-    recompute_tile<MODE, ADDMODE, STAGE>(T, hs, cb, tq, tmax, smem, lane);
+    recompute_tile<MODE, ADDMODE, STAGE, RT>(T, hs, cb, tq, tmax, tq + tmax, smem, lane);
     __syncwarp();
-    walk_tile(smem, row0, col0, i, j, W, a.pxy, a.pgap, lane);
+    walk_tile<RT>(smem, row0, col0, i, j, W, a.pxy, a.pgap, lane);
     __syncwarp();
   }
-  finish_pair(a, T, p, i, j, W, lane);
+  finish_pair<32>(a, T, p, i, j, W, lane, 0xffffffffu, 0);
+}
+
+// Two pairs per warp, one per half warp (jobs with many pairs): 16 lanes x 8 rows per tile.  The
+// wavefront ramp of a tile costs 15 steps instead of 31, and both halves share every issued
+// instruction of the recompute (the step loop runs in lockstep over max(steps) of the two tiles;
+// neighbouring pairs of a batch have similar lengths: they are laid out longest first).  The walks
+// of the two halves diverge and run one after the other.
+constexpr int HALF_TILE_BYTES = (tile_smem_bytes(true) + 15) & ~15;
+template <int MODE, int ADDMODE>
+__global__ void __launch_bounds__(32) traceback_tiles_half_kernel(const TracebackArgs a) {
+  constexpr int RT = RT_HALF, LN = 16;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int half = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const uint32_t p0 = 2u * blockIdx.x;
+  const bool valid = p0 + half < a.npairs;
+  const uint32_t p = valid ? p0 + half : p0;
+  const PairDesc P = a.pairs[p];
+  const TileCtx T = make_ctx<MODE>(a, P);
+  uint8_t *tile = smem + half * HALF_TILE_BYTES;
+  PathOut W{a.out + P.out_off, a.out + P.out_off + P.cap, T.m + T.n, 0};
+  int i = valid ? T.m : 0, j = valid ? T.n : 0;
+  for (;;) {
+    const bool active = i > 0 && j > 0;
+    if (!__any_sync(0xffffffffu, active)) break;
+    int hs = 0, cb = 0, tq = 0, tmax = -1;
+    if (active) {
+      hs = (i - 1) / TILE_ROWS;
+      cb = (j - 1) / (4 * CKQ);
+      tq = ((j - 1 - cb * 4 * CKQ) >> 2) + 1;
+      tmax = (i - 1 - hs * TILE_ROWS) / RT;
+    }
+    const int mine = active ? tq + tmax : 0;
+    const int nsteps = max(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
+    recompute_tile<MODE, ADDMODE, true, RT>(T, hs, cb, tq, tmax, nsteps, tile, lane);
+    __syncwarp();
+    if (active) walk_tile<RT>(tile, hs * TILE_ROWS, cb * 4 * CKQ, i, j, W, a.pxy, a.pgap, lane);
+    __syncwarp();
+  }
+  if (valid) finish_pair<LN>(a, T, p, i, j, W, lane, 0xffffu << (16 * half), 16 * half);
 }
 
 // Four warps per pair (jobs of a few long pairs, where one warp per pair leaves the GPU idle and
@@ -374,12 +425,13 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
   }
   __syncthreads();
   auto full_tq = [&](int cb) { return min(CKQ, T.nq - cb * CKQ); };
+  constexpr int RT = RT_WARP;
   auto full_tmax = [&](int hs) { return min(31, (T.m - 1 - hs * TILE_ROWS) / RT); };
   // first tile: warp 1 computes it in full
   {
     const int hs = (T.m - 1) / TILE_ROWS, cb = (T.n - 1) / (4 * CKQ);
     if (warp == 1) {
-      recompute_tile<MODE, ADDMODE, true>(T, hs, cb, full_tq(cb), full_tmax(hs), smem, lane);
+      recompute_tile<MODE, ADDMODE, true, RT>(T, hs, cb, full_tq(cb), full_tmax(hs), full_tq(cb) + full_tmax(hs), smem, lane);
       if (lane == 0) {
         s_tag[0][0] = hs;
         s_tag[0][1] = cb;
@@ -424,8 +476,8 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
     __syncthreads();  // everybody has read the tags before they change
     if (warp == 0) {
       int wi = i, wj = j;
-      walk_tile(smem + (size_t)cur * LONG_TILE_BYTES, hs * TILE_ROWS, cb * 4 * CKQ, wi, wj, W, a.pxy, a.pgap,
-                lane);
+      walk_tile<RT>(smem + (size_t)cur * LONG_TILE_BYTES, hs * TILE_ROWS, cb * 4 * CKQ, wi, wj, W, a.pxy, a.pgap,
+                    lane);
       if (lane == 0) {
         s_i = wi;
         s_j = wj;
@@ -433,8 +485,9 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
     } else {
       const int c = warp - 1;
       if (target[c] >= 0) {
-        recompute_tile<MODE, ADDMODE, true>(T, cand_hs[c], cand_cb[c], full_tq(cand_cb[c]), full_tmax(cand_hs[c]),
-                                            smem + (size_t)target[c] * LONG_TILE_BYTES, lane);
+        recompute_tile<MODE, ADDMODE, true, RT>(T, cand_hs[c], cand_cb[c], full_tq(cand_cb[c]), full_tmax(cand_hs[c]),
+                                                full_tq(cand_cb[c]) + full_tmax(cand_hs[c]),
+                                                smem + (size_t)target[c] * LONG_TILE_BYTES, lane);
         if (lane == 0) {
           s_tag[target[c]][0] = cand_hs[c];
           s_tag[target[c]][1] = cand_cb[c];
@@ -443,7 +496,7 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
     }
     __syncthreads();
   }
-  if (warp == 0) finish_pair(a, T, p, s_i, s_j, W, lane);
+  if (warp == 0) finish_pair<32>(a, T, p, s_i, s_j, W, lane, 0xffffffffu, 0);
 }
 
 template <int MODE, int ADDMODE>
@@ -454,6 +507,8 @@ static cudaError_t launch_tiles(const TracebackArgs &args, cudaStream_t stream) 
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     traceback_tiles_long_kernel<MODE, ADDMODE><<<args.npairs, 128, smem, stream>>>(args);
+  } else if (args.half_warp) {
+    traceback_tiles_half_kernel<MODE, ADDMODE><<<(args.npairs + 1) / 2, 32, 2 * HALF_TILE_BYTES, stream>>>(args);
   } else {
     constexpr bool STAGE = SEQALK_TB_STAGE != 0;
     traceback_tiles_kernel<MODE, ADDMODE, STAGE><<<args.npairs, 32, tile_smem_bytes(STAGE), stream>>>(args);
