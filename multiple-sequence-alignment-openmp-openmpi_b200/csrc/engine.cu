@@ -462,7 +462,7 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
                                 : 4ull * (uint64_t)macro_cols(n) + 4;
     if (fill16_shift_) brow_ints += pair_base_log_ints(ns, n);  // base logs of the strip pairs, behind the kept rows
     // directions, or (tile mode) the column checkpoints [nq / CKQ][rows padded to the strips]
-    const uint64_t db = tiles_ ? (uint64_t)(macro_cols(n) / CKQ) * geo.mpad * 4 + 32
+    const uint64_t db = tiles_ ? ck_region_bytes(macro_cols(n), geo.mpad, fill16_shift_ != 0) + 32
                                : (uint64_t)ns * strip_dir_bytes(n, R);
     // what counts against the budget: directions, or (tile mode) checkpoints + kept rows
     const uint64_t bb = tiles_ ? db + brow_ints * 4 : db;
@@ -680,7 +680,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       hp[p] = d;
       hs[p] = result_slots_.empty() ? (uint32_t)t_index : result_slots_[t_index];
       if (tiles_) {
-        dir_off += round_up((uint64_t)(macro_cols(d.n) / CKQ) * d.mpad * 4, 32);  // 256-bit checkpoint stores
+        dir_off += round_up(ck_region_bytes(macro_cols(d.n), d.mpad, fill16_shift_ != 0), 32);  // 256-bit checkpoint stores
         brow_off += (uint64_t)(d.mpad / TILE_ROWS) * (4ull * (uint64_t)macro_cols(d.n) + 4);
         if (fill16_shift_) brow_off += pair_base_log_ints((uint32_t)d.nstrips, d.n);
       } else {
@@ -698,7 +698,34 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     // pairs of the three-level geometry with 16 rows per half lane, then the 512-row ones), after
     // all their predecessors have finished.
     size_t n_main = 0, n_mid = 0, n_half = 0;
-    {
+    // packed fill: one persistent launch takes the main strip pairs and the shorter last ones
+    // (SEQALK_FILL16_SPLIT=1: one launch per strip height, as the 32-bit fill does)
+    static const bool split16 = [] {
+      const char *e = std::getenv("SEQALK_FILL16_SPLIT");
+      return e && std::atoi(e) != 0;
+    }();
+    const bool one_launch = fill16_shift_ && !split16;
+    if (one_launch) {
+      // one queue for every strip pair of the batch, critical path first: ordered by the DP cells
+      // from the strip pair's first row to the end of its pair (a predecessor has more of them, so
+      // it is still claimed earlier; the last tasks of the queue are the smallest last strip pairs)
+      queue_keys_.clear();
+      for (size_t p = 0; p < B.count; ++p) {
+        const int ns = hp[p].nstrips, nm = main_strips(ns, hp[p].half_last);
+        for (int s = 0; s < ns; ++s) {
+          int row_base;
+          if (s < nm) row_base = s * 64 * main_rp_;
+          else if (main_rp_ == 32 && (hp[p].half_last & 2) && s == nm) row_base = nm * 2048;
+          else row_base = (int)hp[p].mpad - 512;
+          const uint64_t rem = (uint64_t)(hp[p].mpad - (uint32_t)row_base) * (uint64_t)hp[p].n;
+          queue_keys_.push_back({rem, ((uint64_t)p << 32) | (uint32_t)s});
+        }
+      }
+      std::sort(queue_keys_.begin(), queue_keys_.end(), [](const std::pair<uint64_t, uint64_t> &a, const std::pair<uint64_t, uint64_t> &c) {
+        return a.first != c.first ? a.first > c.first : a.second < c.second;
+      });
+      for (const auto &kv : queue_keys_) ht[n_main++] = StripTask{(uint32_t)(kv.second >> 32), (uint32_t)kv.second};
+    } else {
       static const bool by_remaining = [] {
         const char *e = std::getenv("SEQALK_QUEUE_REMAINING");  // 0: plain (strip, pair) order
         return !e || std::atoi(e) != 0;
@@ -755,10 +782,13 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.rebase_shift = fill16_shift_;
     fa.main_rp = main_rp_;
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 0], st));
-    if (fill16_shift_)
+    if (one_launch) {
+      SEQALK_CUDA(launch_fill16(fa, 100 + main_rp_, variant_.minb, sm_count_, st));
+    } else if (fill16_shift_) {
       SEQALK_CUDA(launch_fill16(fa, main_rp_, variant_.minb, sm_count_, st));
-    else
+    } else {
       SEQALK_CUDA(launch_fill(fa, variant_, sm_count_, st));
+    }
     if (n_mid) {  // second launch (three-level geometry): the 1024-row strip pairs
       FillArgs fm = fa;
       fm.tasks = fa.tasks + n_main;
@@ -810,7 +840,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     ta.long_pairs = few_pairs_ ? 1 : 0;
     ta.strip_scan = strip_scan_ ? 1 : 0;
     if (const char *e = std::getenv("SEQALK_TB_LONG")) ta.long_pairs = std::atoi(e) ? 1 : 0;
-    ta.half_warp = 0;  // measured slower at 256-column tiles (11 instead of 23 warps per SM), profiles/experiments
+    ta.half_warp = 1;  // two pairs per warp (SEQALK_TB_HALF=0: one warp per pair)
     if (const char *e = std::getenv("SEQALK_TB_HALF")) ta.half_warp = std::atoi(e) ? 1 : 0;
     if (!fill_only) SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));

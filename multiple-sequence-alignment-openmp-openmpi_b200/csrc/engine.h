@@ -14,6 +14,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 #include "seqalk_kernels.h"
 
@@ -154,6 +155,7 @@ class DeviceWorker {
   std::vector<TaskIJ> tasks_;
   std::vector<uint32_t> result_slots_;
   std::vector<uint32_t> order_;  // scratch: longest-first order of the current batch
+  std::vector<std::pair<uint64_t, uint64_t>> queue_keys_;  // scratch: (cells to the end of the pair, pair << 32 | strip)
   std::vector<Batch> batches_;
   int pxy_ = 0, pgap_ = 0;
   FillVariant variant_;

@@ -36,9 +36,11 @@
 // reads a tile's left edge):
 //   * kept rows (every TILE_ROWS DP rows): absolute int32 H', converted with IDP.2A — also the
 //     hand-off row to the next strip pair and the carrier of the corner H'[m][n];
-//   * column checkpoints (every CKQ macro columns): the packed registers as they are; per
-//     checkpoint two images [low halves valid | high halves valid] of mpad/2 words, since the two
-//     halves reach a checkpoint column 32 steps apart; the traceback unpacks with the logged base.
+//   * column checkpoints (every CKQ macro columns): the packed registers as they are, images of
+//     mpad/2 words.  CKQ = 64: per checkpoint two images [low halves valid | high halves valid],
+//     since the two halves reach a checkpoint column 32 steps apart; CKQ = 32: both halves are at a
+//     checkpoint column at the same step, image e = [rows of A at checkpoint e | rows of B at
+//     checkpoint e - 1].  The traceback unpacks with the logged base.
 #include <algorithm>
 
 #include "fill_core.cuh"
@@ -48,7 +50,7 @@ namespace seqalk {
 namespace {
 
 constexpr int F16_THREADS = 128;
-static_assert(CKQ == 64, "the two halves of a register reach checkpoint columns 32 steps apart");
+static_assert(CKQ == 64 || CKQ == 32, "the two halves of a register reach a macro column 32 steps apart");
 constexpr unsigned SEL_NULL = 0xCC88CC88u;  // both columns of a selector word: cost 0 in both halves
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
@@ -287,10 +289,23 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
       // branch (every lane once per 32 steps), so it is kept short: consecutive stores of a lane go
       // to consecutive images (k, low halves), (k, high halves), (k+1, low halves), ...
       if (((qcA + 1) & 31) == 0) {
-        const int ckcol = (qcA + 1) >> 5;  // even: the low halves are at a checkpoint column, odd: the high halves
-        const int qc = (ckcol & 1) ? qcA - 32 : qcA;
-        if (ckcol >= 2 && qc < nq) {
-          uint32_t *dst = ck + (int64_t)(ckcol - 2) * (int64_t)halfwords;
+        const int ckcol = (qcA + 1) >> 5;
+        bool store;
+        uint32_t *dst;
+        if constexpr (CKQ == 64) {
+          // even: the low halves are at a checkpoint column, odd: the high halves
+          const int qc = (ckcol & 1) ? qcA - 32 : qcA;
+          store = ckcol >= 2 && qc < nq;
+          dst = ck + (int64_t)(ckcol - 2) * (int64_t)halfwords;
+        } else {
+          // a checkpoint every 32 macro columns: both halves are at one — the low halves at
+          // checkpoint ckcol - 1, the high halves at checkpoint ckcol - 2 — so image ckcol - 1 holds
+          // [rows of A at checkpoint ckcol - 1 | rows of B at checkpoint ckcol - 2]; stored while a
+          // tile to the right of either column exists
+          store = ckcol >= 1 && (qcA + 1 < nq || (ckcol >= 2 && qcA - 31 < nq));
+          dst = ck + (int64_t)(ckcol - 1) * (int64_t)halfwords;
+        }
+        if (store) {
 #pragma unroll
           for (int r8 = 0; r8 < RP / 8; ++r8)
             asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * r8), "r"(h[8 * r8]),
@@ -337,6 +352,34 @@ __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_kernel(const FillArg
   }
 }
 
+// One persistent kernel for ALL strip pairs of a batch: the main ones (64 * MAINRP rows) and a
+// pair's shorter last ones (1024 rows in the three-level geometry, 512 rows), which wait for their
+// predecessor through the same progress counters as every other strip pair.  One queue, one
+// ramp-down per batch instead of three (the tail launches of a small batch — one GPU's share of a
+// chunk on 8 GPUs — are shorter than one wave of warps).
+template <int MAINRP, int MINB>
+__global__ void __launch_bounds__(F16_THREADS, MINB) fill16_all_kernel(const FillArgs a) {
+  __shared__ uint2 s_sel[F16_THREADS / 32][128];
+  __shared__ int4 s_top[F16_THREADS / 32][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(a.counter, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.ntasks) break;
+    const StripTask task = a.tasks[t];
+    const PairDesc P = a.pairs[task.pair];
+    const int s = (int)task.strip;
+    const int nmain = main_strips(P.nstrips, P.half_last);
+    if (s < nmain)
+      process_strip_pair<MAINRP>(a, P, s, s * (64 * MAINRP), lane, s_sel[warp], s_top[warp]);
+    else if (MAINRP == 32 && (P.half_last & 2) && s == nmain)
+      process_strip_pair<16>(a, P, s, nmain * 2048, lane, s_sel[warp], s_top[warp]);
+    else
+      process_strip_pair<8>(a, P, s, (int)P.mpad - 512, lane, s_sel[warp], s_top[warp]);
+  }
+}
+
 // ---- selector streams, one per sequence (built once per load): entry e = two words, 16 bits per
 // DP column c of macro column e: nibbles [code of y[4e+c] | 8, 8, 4 + code of y[4(e-32)+c] | 0xC, 0xC]
 __global__ void build_sel16_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ sel16,
@@ -361,7 +404,13 @@ __global__ void build_sel16_kernel(const uint8_t *__restrict__ codes, uint8_t *_
 }
 
 typedef void (*Fill16Ptr)(const FillArgs);
+Fill16Ptr pick16_all(int rp, int minb) {
+  if (rp == 32) return minb == 3 ? fill16_all_kernel<32, 3> : fill16_all_kernel<32, 4>;
+  if (rp == 16) return minb == 5 ? fill16_all_kernel<16, 5> : fill16_all_kernel<16, 6>;
+  return nullptr;
+}
 Fill16Ptr pick16(int rp, int minb) {
+  if (rp >= 100) return pick16_all(rp - 100, minb);  // 100 + main rp: the one-launch kernel
   // 32 rows per half lane: 128 registers without spills = 4 CTAs per SM (cfg4 fill 4.14 s; 3 CTAs: 4.20 s)
   if (rp == 32) return minb == 3 ? fill16_kernel<32, 3> : fill16_kernel<32, 4>;
   if (rp == 16) {

@@ -16,11 +16,20 @@ struct FillVariant {
   bool emit = true; // true: directions mode (2-bit codes to HBM); false: tile mode (scores +
                     // checkpoints, directions recomputed by the traceback for the tiles it visits)
 };
-// tile mode: a column checkpoint every CKQ macro columns (4*CKQ DP columns), a row every TILE_ROWS rows
+// tile mode: a column checkpoint every CKQ macro columns (4*CKQ DP columns), a row every TILE_ROWS rows.
+// 32 = 128 x 128 tiles: free for the packed fill (both halves of a register reach a checkpoint column
+// at the same step) and, with two pairs per warp in the traceback, 25 % less traceback time on
+// BASELINE config 4 than 128 x 256 tiles (811 -> 608 ms); the 32-bit fill pays ~5 % for it.
 #ifndef SEQALK_CKQ
-#define SEQALK_CKQ 64
+#define SEQALK_CKQ 32
 #endif
 constexpr int CKQ = SEQALK_CKQ;  // 64 or 32
+// bytes of a pair's column checkpoints: int32 fill [nq / CKQ][mpad]; packed fill: images of mpad / 2
+// words (fill16.cu) — two per checkpoint at CKQ = 64, ceil(nq / 32) at CKQ = 32
+__host__ __device__ inline uint64_t ck_region_bytes(int nq, uint64_t mpad, bool packed) {
+  if (packed && CKQ == 32) return (uint64_t)((nq + 31) / 32) * mpad * 2;
+  return (uint64_t)(nq / CKQ) * mpad * 4;
+}
 #ifndef SEQALK_TILE_ROWS
 #define SEQALK_TILE_ROWS 128
 #endif

@@ -1,15 +1,16 @@
 // traceback_tiles.cu — traceback for the tile mode: directions are NOT read from HBM but
-// recomputed, one TILE_ROWS-row x (4*CKQ)-column tile (128 x 256) at a time, only for the tiles the optimal path
-// visits (about m / 128 + n / 256 of them), from the checkpoints the score-only fill left behind:
+// recomputed, one TILE_ROWS-row x (4*CKQ)-column tile (128 x 128) at a time, only for the tiles the optimal path
+// visits (about m / 128 + n / 128 of them), from the checkpoints the score-only fill left behind:
 // one row of H' every TILE_ROWS DP rows and one column of H' every 4*CKQ DP columns.
 //
 // Same reference semantics as traceback.cu (submit/xuliny-seqalkway.cpp:502-558, :191-214):
 // the recompute runs the very same per-cell update as the fill (fill_core.cuh, EMIT = true), so
 // the 2-bit codes — and with them the tie-breaking — are identical to the directions mode.
 //
-// One warp per pair.  Per tile: lane t owns RT rows, the warp sweeps the needed macro columns
-// as a skewed wavefront (exactly like the fill) writing the codes to shared memory, then walks
-// the path inside the tile until it leaves through the top or the left edge.
+// Half a warp per pair (jobs with many pairs; a whole warp + three look-ahead warps for jobs of a
+// few long pairs).  Per tile: lane t owns RT rows, the lanes sweep the needed macro columns as a
+// skewed wavefront (exactly like the fill) writing the codes to shared memory, then walk the path
+// inside the tile until it leaves through the top or the left edge.
 #include "fill_core.cuh"
 
 namespace seqalk {
@@ -140,7 +141,9 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
       const int32_t *blog = T.brow + (uint64_t)(T.mpad / TILE_ROWS) * T.bstride +
                             (uint64_t)s * (uint64_t)base_log_entries(T.nq, T.ck16);
       const int base = __ldcg(blog + (step >> T.ck16));
-      const uint32_t *img = reinterpret_cast<const uint32_t *>(T.ck) + ((uint64_t)(cb - 1) * 2 + half) * (T.mpad / 2);
+      // CKQ = 64: images (checkpoint, half); CKQ = 32: image e = [A rows at checkpoint e | B rows at e - 1]
+      const uint64_t image = CKQ == 64 ? (uint64_t)(cb - 1) * 2 + half : (uint64_t)(cb - 1) + half;
+      const uint32_t *img = reinterpret_cast<const uint32_t *>(T.ck) + image * (T.mpad / 2);
       const uint4 *src = reinterpret_cast<const uint4 *>(img + (sp0 >> 1) + (rem - half * (sp_rows >> 1)));
 #pragma unroll
       for (int r4 = 0; r4 < RT / 4; ++r4) {
@@ -169,9 +172,8 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
     else
       reinterpret_cast<uint32_t *>(tile + TILE_DIR_BYTES)[lane] =
           r0 < T.m ? *reinterpret_cast<const uint32_t *>(T.xs + r0) : 0u;
-    static_assert((4 * CKQ) % (8 * LN) == 0, "8 y characters per lane and round");
 #pragma unroll
-    for (int c = lane * 8; c < 4 * CKQ; c += 8 * LN)
+    for (int c = lane * 8; c < 4 * CKQ; c += 8 * LN)  // 8 y characters per lane and round
       *reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES + TILE_ROWS + c) =
           col0 + c < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + col0 + c) : 0ull;
   }
@@ -367,7 +369,10 @@ __global__ void __launch_bounds__(32) traceback_tiles_kernel(const TracebackArgs
 // wavefront ramp of a tile costs 15 steps instead of 31, and both halves share every issued
 // instruction of the recompute (the step loop runs in lockstep over max(steps) of the two tiles;
 // neighbouring pairs of a batch have similar lengths: they are laid out longest first).  The walks
-// of the two halves diverge and run one after the other.
+// of the two halves run together as long as their control flow agrees.
+// Measured (one B200, same box): cfg4 traceback 811 ms (one warp per pair, 128 x 256 tiles) ->
+// 743 ms (128 x 128 tiles) -> 608 ms (this kernel, 22 CTAs per SM); with 128 x 256 tiles this kernel
+// was SLOWER (870 ms): 11 CTAs per SM by shared memory, issue slots 64 % busy instead of 82 %.
 constexpr int HALF_TILE_BYTES = (tile_smem_bytes(true) + 15) & ~15;
 template <int MODE, int ADDMODE>
 __global__ void __launch_bounds__(32) traceback_tiles_half_kernel(const TracebackArgs a) {

@@ -12,7 +12,7 @@ T0 = None
 pxy, pgap, genes = workloads.make(name)
 lens = [len(g) for g in genes]
 T = len(genes) * (len(genes) - 1) // 2
-nchunks = int(sys.argv[3]) if len(sys.argv) > 3 else max(1, min(8, T // 32768))
+nchunks = int(sys.argv[3]) if len(sys.argv) > 3 else max(1, min(14, T // 16384))
 runs = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 parts = pkg.partition_chunks(lens, nranks, nchunks)
 ids = np.concatenate([parts[c][0] for c in range(nchunks)])
