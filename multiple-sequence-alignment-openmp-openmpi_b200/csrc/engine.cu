@@ -215,6 +215,16 @@ DeviceWorker::DeviceWorker(int device) : dev_(device) {
   SEQALK_CUDA(cudaStreamCreateWithPriority(&fill_stream_, cudaStreamNonBlocking, prio_lo));
   SEQALK_CUDA(cudaStreamCreateWithPriority(&post_stream_, cudaStreamNonBlocking, prio_hi));
   SEQALK_CUDA(cudaStreamCreateWithPriority(&fill2_stream_, cudaStreamNonBlocking, prio_lo));
+  for (int i = 2; i < nslots_; ++i) {
+    cudaStream_t st = nullptr;
+    SEQALK_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_lo));
+    more_streams_.push_back(st);
+  }
+  for (int i = 0; i < nslots_; ++i) {
+    cudaStream_t st = nullptr;
+    SEQALK_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
+    pipe_post_streams_.push_back(st);
+  }
   for (Slot &s : slots_) {
     SEQALK_CUDA(cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
     SEQALK_CUDA(cudaEventCreateWithFlags(&s.fill_done, cudaEventDisableTiming));
@@ -223,7 +233,7 @@ DeviceWorker::DeviceWorker(int device) : dev_(device) {
 }
 
 int DeviceWorker::slots_from_env() {
-  int n = 2;
+  int n = 3;  // tile mode: three overlapped batch pipelines (dirs mode: buffer sets)
   if (const char *e = std::getenv("SEQALK_SLOTS")) n = std::max(1, std::min(4, std::atoi(e)));
   return n;
 }
@@ -251,6 +261,8 @@ DeviceWorker::~DeviceWorker() {
   if (fill_stream_) cudaStreamDestroy(fill_stream_);
   if (post_stream_) cudaStreamDestroy(post_stream_);
   if (fill2_stream_) cudaStreamDestroy(fill2_stream_);
+  for (cudaStream_t st : more_streams_) cudaStreamDestroy(st);
+  for (cudaStream_t st : pipe_post_streams_) cudaStreamDestroy(st);
   release(seq_);
   release(codes_);
   release(sel16_);
@@ -371,20 +383,22 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   }
   variant_.emit = !tiles_;
   {  // checkpoint / direction budget per buffer set (larger batches = fewer kernel tails), capped
-     // by the device's memory.  dirs mode double-buffers the big arrays (fill of batch b+1 runs
-     // beside the traceback of batch b): 56 GB each; tile mode runs its stages back to back on
-     // one stream and needs a single set: 104 GB (136 GB: 18 instead of 24 batches on cfg4 and
-     // -0.6 % job time in a same-box A/B; not taken, to leave memory for the caller).
+     // by the device's memory.  dirs mode: 56 GB per set (the fill of batch b+1 runs beside the
+     // traceback of batch b).  Tile mode: one set per pipeline — 3 x 40 GB by default
+     // (SEQALK_SLOTS / SEQALK_DIR_BUDGET_GB), 104 GB without overlap.
     SEQALK_CUDA(cudaSetDevice(dev_));
     size_t free_b = 0, total_b = 0;
     SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    // tile mode: the stages of a batch run back to back on one stream; with two pipelines (two
-    // sets of the big arrays, two streams) consecutive batches overlap, so the tail of one batch's
-    // fill / traceback / digest is filled by the next batch's kernels (SEQALK_OVERLAP=0: one set)
+    // tile mode: consecutive batches go to different pipelines (own set of the big arrays, own
+    // streams), so the tail of one batch's fill / traceback / digest is filled by the next
+    // batches' kernels (SEQALK_OVERLAP=0: one set, stages back to back).  One GPU's share of an
+    // 8-GPU cfg4 job, emulated on one GPU (scripts/shard_span.py): 704 ms without overlap, 640 ms
+    // with two pipelines, 610 ms with three and the traceback / digest on high-priority streams.
     overlap_ = tiles_ && nslots_ >= 2;
     if (const char *e = std::getenv("SEQALK_OVERLAP")) overlap_ = overlap_ && std::atoi(e) != 0;
-    const int nbig = tiles_ ? (overlap_ ? 2 : 1) : nslots_;
-    double budget_gb = tiles_ ? (overlap_ ? 52.0 : 104.0) : 56.0;
+    const int nbig = tiles_ ? (overlap_ ? nslots_ : 1) : nslots_;
+    // three pipelines of 40 GB: a tenth of an 8-GPU job's tasks per GPU still fits one batch
+    double budget_gb = tiles_ ? (nbig >= 3 ? 40.0 : 104.0 / nbig) : 56.0;
     if (const char *e = std::getenv("SEQALK_DIR_BUDGET_GB")) budget_gb = std::atof(e);
     dir_budget_ = (size_t)(budget_gb * (double)(1ull << 30));
     // our own (cached) buffers count as available
@@ -622,7 +636,8 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     // buffers stay per slot: the host fills the next batch's staging while this one runs)
     Slot &G = (tiles_ && !overlap_) ? slots_[0] : S;
     // the batch's stream (tile mode): its whole pipeline runs there
-    cudaStream_t tile_stream = (overlap_ && (b % nslots_) % 2 == 1) ? fill2_stream_ : fill_stream_;
+    const int pipe = overlap_ ? (int)(b % nslots_) : 0;
+    cudaStream_t tile_stream = pipe == 0 ? fill_stream_ : pipe == 1 ? fill2_stream_ : more_streams_[(size_t)pipe - 2];
     // ---- size device buffers (for the largest batch of the job: at most one allocation)
     ensure(S.pairs, need_.count * sizeof(PairDesc));
     ensure(S.tasks, (size_t)need_.nstrips * sizeof(StripTask));
@@ -816,7 +831,14 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     SEQALK_CUDA(cudaEventRecord(S.fill_done, st));
     // ---- enqueue: post stream (high priority; runs under the next batch's fill).  In tile
     // mode the traceback is a heavy kernel of its own: the stages run back to back instead.
-    st = tiles_ ? tile_stream : post_stream_;
+    // Tile mode, overlapped pipelines: traceback + digest of a batch go to the pipeline's own
+    // HIGH-priority stream, so that when SMs free up they are placed before the CTAs of a later
+    // batch's persistent fill (otherwise a batch's results wait for the fill after next)
+    static const bool post_prio = [] {
+      const char *e = std::getenv("SEQALK_POST_PRIORITY");
+      return !e || std::atoi(e) != 0;
+    }();
+    st = tiles_ ? ((overlap_ && post_prio) ? pipe_post_streams_[(size_t)pipe] : tile_stream) : post_stream_;
     SEQALK_CUDA(cudaStreamWaitEvent(st, S.fill_done, 0));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 2], st));
 
@@ -905,6 +927,8 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
   SEQALK_CUDA(cudaStreamSynchronize(post_stream_));
   SEQALK_CUDA(cudaStreamSynchronize(fill2_stream_));
+  for (cudaStream_t st : more_streams_) SEQALK_CUDA(cudaStreamSynchronize(st));
+  for (cudaStream_t st : pipe_post_streams_) SEQALK_CUDA(cudaStreamSynchronize(st));
   for (Slot &S : slots_) S.staged_pending = S.post_pending = false;
   if (batch_end == batches_.size() && !scores_only) verify_check();
   ran_ = true;

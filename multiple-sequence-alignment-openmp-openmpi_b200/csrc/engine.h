@@ -147,6 +147,8 @@ class DeviceWorker {
   std::vector<Slot> slots_;
   cudaStream_t fill_stream_ = nullptr, post_stream_ = nullptr;
   cudaStream_t fill2_stream_ = nullptr;  // tile mode with overlap: batches alternate between fill_stream_ and this one
+  std::vector<cudaStream_t> more_streams_;  // ... and these, with more than two pipelines (SEQALK_SLOTS)
+  std::vector<cudaStream_t> pipe_post_streams_;  // tile mode with overlap: traceback + digest of pipeline p (high priority)
   bool overlap_ = false;  // tile mode: two full pipelines (buffer sets + streams), so that a batch's kernel tails are
                           // filled by the next batch's kernels
   DevBuf seq_, codes_, sel16_, seqmeta_;
