@@ -84,7 +84,7 @@ constexpr int tile_smem_bytes(bool stage) { return TILE_DIR_BYTES + TILE_CHAR_BY
 #endif
 
 // Recomputes the directions of tile (hs, cb), macro columns [0, tq) and lanes [0, tmax], into
-// `tile`, by a group of LN = TILE_ROWS / RT lanes (`lane` = index inside the group; every lane of
+// `tile`, by a group of LN lanes owning RT rows each (`lane` = index inside the group; every lane of
 // the WARP must call this together, with the same `nsteps` >= tq + tmax: the groups of a warp run
 // the step loop in lockstep, each on its own tile).  Same sweep as the fill: lane t owns RT rows,
 // trails lane t-1 by one macro column; left edge = column checkpoint cb-1, top edge = kept row hs-1.
@@ -92,10 +92,10 @@ constexpr int tile_smem_bytes(bool stage) { return TILE_DIR_BYTES + TILE_CHAR_BY
 // STAGE: the group first copies the top edge to shared memory with a few wide loads; otherwise
 // lane 0 fetches it from global memory one macro column ahead, which exposes the load latency on
 // every step unless other warps cover it.
-template <int MODE, int ADDMODE, bool STAGE, int RT>
+template <int MODE, int ADDMODE, bool STAGE, int RT, int LN = TILE_ROWS / RT>
 __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb, int tq, int tmax, int nsteps,
                                                uint8_t *tile, int lane) {
-  constexpr int LN = TILE_ROWS / RT;  // lanes per tile
+  static_assert(LN * RT <= TILE_ROWS, "LN lanes x RT rows: the tile, or (LN * RT < TILE_ROWS) its upper part");
   constexpr int WPE = RT / 4;         // 32-bit words of direction codes per lane and macro column
   static_assert(RT == 8 || RT == 4, "rows per lane");
   const unsigned FULL = 0xffffffffu;
@@ -259,10 +259,9 @@ __device__ __forceinline__ void emit_steps(const uint8_t *sxb, const uint8_t *sy
 // so that the current cell's code sits in the top two bits (a step is: read the code, rotate by
 // a table look-up, move, append the code to the history).  The history is emitted by up to 15
 // lanes at once (emit_steps).
-template <int RT>
+template <int RT, int LN = TILE_ROWS / RT>  // LN lanes x RT rows recomputed the tile (layout of the code words)
 __device__ __forceinline__ void walk_tile(const uint8_t *tile, int row0, int col0, int &i, int &j, PathOut &W,
                                           int pxy, int pgap, int lane) {
-  constexpr int LN = TILE_ROWS / RT;  // lanes that recomputed the tile (layout of the code words)
   constexpr int WPE = RT / 4;
   constexpr int CW = 16 / RT;         // columns of a word's block
   constexpr int MAXB = RT + CW - 1;   // most steps inside one block
@@ -390,18 +389,30 @@ __global__ void __launch_bounds__(32) traceback_tiles_half_kernel(const Tracebac
   for (;;) {
     const bool active = i > 0 && j > 0;
     if (!__any_sync(0xffffffffu, active)) break;
-    int hs = 0, cb = 0, tq = 0, tmax = -1;
+    int hs = 0, cb = 0, tq = 0, li = -1;
     if (active) {
       hs = (i - 1) / TILE_ROWS;
       cb = (j - 1) / (4 * CKQ);
       tq = ((j - 1 - cb * 4 * CKQ) >> 2) + 1;
-      tmax = (i - 1 - hs * TILE_ROWS) / RT;
+      li = i - 1 - hs * TILE_ROWS;  // row of the entry cell inside the tile
     }
-    const int mine = active ? tq + tmax : 0;
-    const int nsteps = max(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
-    recompute_tile<MODE, ADDMODE, true, RT>(T, hs, cb, tq, tmax, nsteps, tile, lane);
-    __syncwarp();
-    if (active) walk_tile<RT>(tile, hs * TILE_ROWS, cb * 4 * CKQ, i, j, W, a.pxy, a.pgap, lane);
+    // both tiles entered in their upper half: 4 rows per lane keep twice as many lanes busy
+    if (__all_sync(0xffffffffu, li < TILE_ROWS / 2)) {
+      constexpr int RS = RT / 2;
+      const int tmax = active ? li / RS : -1;
+      const int mine = active ? tq + tmax : 0;
+      const int nsteps = max(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
+      recompute_tile<MODE, ADDMODE, true, RS, LN>(T, hs, cb, tq, tmax, nsteps, tile, lane);
+      __syncwarp();
+      if (active) walk_tile<RS, LN>(tile, hs * TILE_ROWS, cb * 4 * CKQ, i, j, W, a.pxy, a.pgap, lane);
+    } else {
+      const int tmax = active ? li / RT : -1;
+      const int mine = active ? tq + tmax : 0;
+      const int nsteps = max(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
+      recompute_tile<MODE, ADDMODE, true, RT, LN>(T, hs, cb, tq, tmax, nsteps, tile, lane);
+      __syncwarp();
+      if (active) walk_tile<RT, LN>(tile, hs * TILE_ROWS, cb * 4 * CKQ, i, j, W, a.pxy, a.pgap, lane);
+    }
     __syncwarp();
   }
   if (valid) finish_pair<LN>(a, T, p, i, j, W, lane, 0xffffu << (16 * half), 16 * half);
