@@ -287,6 +287,19 @@ void DeviceWorker::ensure(DevBuf &b, size_t bytes) {
     e = cudaMalloc(&b.p, want);
   }
   if (e != cudaSuccess) {
+    // the big arrays cached from an earlier job with another buffer configuration (more
+    // pipelines, smaller sets) may be in the way: nothing is in flight here, drop them all — the
+    // slots that are still needed grow theirs again
+    cudaGetLastError();
+    for (Slot &s : slots_)
+      for (DevBuf *o : {&s.brow, &s.dirs, &s.out})
+        if (o != &b && o->p) {
+          release(*o);
+          dropped_cached_ = true;
+        }
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
     char msg[256];
     std::snprintf(msg, sizeof msg, "getMinimumPenalty: device allocation of %zu bytes failed (%s)", want,
                   cudaGetErrorString(e));
@@ -639,16 +652,19 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     const int pipe = overlap_ ? (int)(b % nslots_) : 0;
     cudaStream_t tile_stream = pipe == 0 ? fill_stream_ : pipe == 1 ? fill2_stream_ : more_streams_[(size_t)pipe - 2];
     // ---- size device buffers (for the largest batch of the job: at most one allocation)
-    ensure(S.pairs, need_.count * sizeof(PairDesc));
-    ensure(S.tasks, (size_t)need_.nstrips * sizeof(StripTask));
-    ensure(S.slots, need_.count * sizeof(uint32_t));
-    ensure(S.progress, (size_t)need_.nstrips * sizeof(uint32_t));
-    ensure(G.brow, need_.brow_ints * sizeof(int32_t));
-    ensure(G.dirs, need_.dir_bytes);
-    ensure(G.out, need_.out_bytes + BUFFER_SLACK);
-    ensure(G.align, need_.count * sizeof(PairAlign));
-    ensure(G.cost, need_.count * sizeof(int32_t));
-    ensure(S.counter, 4 * sizeof(uint32_t));
+    do {  // (again if an allocation had to drop cached arrays of this very set)
+      dropped_cached_ = false;
+      ensure(S.pairs, need_.count * sizeof(PairDesc));
+      ensure(S.tasks, (size_t)need_.nstrips * sizeof(StripTask));
+      ensure(S.slots, need_.count * sizeof(uint32_t));
+      ensure(S.progress, (size_t)need_.nstrips * sizeof(uint32_t));
+      ensure(G.brow, need_.brow_ints * sizeof(int32_t));
+      ensure(G.dirs, need_.dir_bytes);
+      ensure(G.out, need_.out_bytes + BUFFER_SLACK);
+      ensure(G.align, need_.count * sizeof(PairAlign));
+      ensure(G.cost, need_.count * sizeof(int32_t));
+      ensure(S.counter, 4 * sizeof(uint32_t));
+    } while (dropped_cached_);
     // ---- build descriptors in pinned staging
     const size_t pairs_bytes = round_up(need_.count * sizeof(PairDesc), 256);
     const size_t tasks_bytes = round_up((size_t)need_.nstrips * sizeof(StripTask), 256);
@@ -715,7 +731,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     size_t n_main = 0, n_mid = 0, n_half = 0;
     // packed fill: one persistent launch takes the main strip pairs and the shorter last ones
     // (SEQALK_FILL16_SPLIT=1: one launch per strip height, as the 32-bit fill does)
-    static const bool split16 = [] {
+    const bool split16 = [] {
       const char *e = std::getenv("SEQALK_FILL16_SPLIT");
       return e && std::atoi(e) != 0;
     }();
@@ -741,7 +757,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       });
       for (const auto &kv : queue_keys_) ht[n_main++] = StripTask{(uint32_t)(kv.second >> 32), (uint32_t)kv.second};
     } else {
-      static const bool by_remaining = [] {
+      const bool by_remaining = [] {
         const char *e = std::getenv("SEQALK_QUEUE_REMAINING");  // 0: plain (strip, pair) order
         return !e || std::atoi(e) != 0;
       }();
@@ -834,7 +850,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     // Tile mode, overlapped pipelines: traceback + digest of a batch go to the pipeline's own
     // HIGH-priority stream, so that when SMs free up they are placed before the CTAs of a later
     // batch's persistent fill (otherwise a batch's results wait for the fill after next)
-    static const bool post_prio = [] {
+    const bool post_prio = [] {
       const char *e = std::getenv("SEQALK_POST_PRIORITY");
       return !e || std::atoi(e) != 0;
     }();

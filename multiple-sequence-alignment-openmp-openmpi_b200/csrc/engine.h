@@ -139,6 +139,7 @@ class DeviceWorker {
   void ensure(DevBuf &b, size_t bytes);
   void ensure_stage(Slot &s, size_t bytes);
   void release(DevBuf &b);
+  bool dropped_cached_ = false;  // ensure() released cached big arrays of other slots to make room
 
   int dev_;
   int sm_count_ = 0;

@@ -303,6 +303,15 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     {"SEQALK_TRACEBACK": "tiles", "SEQALK_FILL_TAB": "0", "SEQALK_FILL_ADD": "1"},
     {"SEQALK_TRACEBACK": "tiles", "SEQALK_FORCE_GENERAL": "1"},
     {"SEQALK_TRACEBACK": "tiles", "SEQALK_DIR_BUDGET_GB": "0.001"},
+    # the many-pair production path on this small job: packed fill (one persistent launch over all
+    # strip pairs) + half-warp tile traceback, and the alternatives kept behind knobs
+    {"SEQALK_FILL_R": "32", "SEQALK_TB_LONG": "0"},
+    {"SEQALK_FILL_R": "32", "SEQALK_TB_LONG": "0", "SEQALK_TB_HALF": "0"},
+    {"SEQALK_FILL_R": "32", "SEQALK_TB_LONG": "0", "SEQALK_FILL16_SPLIT": "1", "SEQALK_QUEUE_REMAINING": "0"},
+    {"SEQALK_FILL_R": "32", "SEQALK_TB_LONG": "0", "SEQALK_FILL16_RP": "16"},
+    {"SEQALK_FILL_R": "32", "SEQALK_TB_LONG": "0", "SEQALK_DIR_BUDGET_GB": "0.001"},
+    {"SEQALK_FILL_R": "32", "SEQALK_TB_LONG": "0", "SEQALK_DIR_BUDGET_GB": "0.001", "SEQALK_SLOTS": "2",
+     "SEQALK_POST_PRIORITY": "0"},
 ], ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
 def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatch, env):
     """Rows per lane (8/16), cost by compare or by 4-letter table, adds on ALU or FMA pipe,
@@ -315,6 +324,8 @@ def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatc
     with seqalk.Job(genes, 3, 2) as job:  # a fresh worker picks the env up
         job.run()
         pen, dig = job.fetch()
+        if env.get("SEQALK_FILL_R") == "32":  # the packed fill really ran
+            assert job.stats().fill_packed16 == 1
     od, op, oh = oracle.all_pairs(genes, 3, 2, want_pair_hashes=True)
     assert np.array_equal(pen, op)
     assert [d.tobytes().hex() for d in dig] == oh
