@@ -155,35 +155,25 @@ struct DeviceArray {
   }
 };
 
-// Chunk c covers task ids [bounds[c], bounds[c+1]).  The host folds chunk c (0.6 - 0.8 us per task,
+// Chunk c covers task ids [bounds[c], bounds[c+1]).  The host folds chunk c (about 0.6 us per task,
 // serial by construction) while the GPUs work on the chunks after it; what stays exposed at the end
 // is  max over c of  fold(chunks >= c) - gpu(chunks > c).
-// With the two overlapped batch pipelines of a GPU (engine.cu) chunks complete in PAIRS: the
-// traceback of chunk 2p only gets SMs when the persistent fill of chunk 2p+1 winds down (8-GPU
-// trace, profiles/r02_n8_chunk_trace.txt: chunks 4 and 5 — 28 % of the tasks — arrived together
-// 140 ms before the end and left 33 ms of fold exposed).  So the schedule is laid out in pairs of
-// equal chunks: body pairs of equal size, then up to four pairs shrinking by 0.6 each — the fold
-// of one pair (0.8 us per task) fits into the GPU time of the next one (>= 1.3 us per task up to
-// 8 GPUs) — so that the exposed part is the fold of the last, smallest pair.
+// A GPU works on up to three chunks at once (overlapped batch pipelines, engine.cu), so a chunk's
+// results arrive two to three chunks after its fill started, and neighbouring chunks arrive together
+// (8-GPU traces in profiles/r02_n8_chunk_trace.txt: with equal body chunks 42 % of the tasks arrived
+// in the last 95 ms and left 23 - 30 ms of fold exposed).  Chunk sizes therefore shrink
+// geometrically from the first one (x 0.8 per chunk): the work in flight — and with it the fold
+// that is left when the GPUs finish — shrinks with them (the last three of 14 chunks hold 4.4 % of
+// the tasks), while the first chunks stay large enough for full-size batches.
 void chunk_bounds(int64_t T, int nchunks, std::vector<int64_t> &b) {
   b.assign((size_t)nchunks + 1, 0);
   if (nchunks >= 4 && T >= 4096) {
-    const int npairs = (nchunks + 1) / 2;  // the last pair is a single chunk when nchunks is odd
-    const int ntaper = std::min(4, npairs - 1);
-    std::vector<double> w((size_t)nchunks);
-    double sum = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      const int p = c / 2;
-      const int k = p - (npairs - ntaper - 1);  // 0 for body pairs, 1.. for the tapered ones
-      double pw = 1.0;
-      for (int i = 0; i < k; ++i) pw *= 0.6;
-      const int in_pair = (2 * p + 1 < nchunks) ? 2 : 1;
-      w[(size_t)c] = pw / in_pair;
-      sum += w[(size_t)c];
-    }
+    double sum = 0, w = 1.0;
+    for (int c = 0; c < nchunks; ++c, w *= 0.8) sum += w;
     double acc = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      acc += w[(size_t)c];
+    w = 1.0;
+    for (int c = 0; c < nchunks; ++c, w *= 0.8) {
+      acc += w;
       b[(size_t)c + 1] = std::max(b[(size_t)c], (int64_t)((double)T * (acc / sum)));
     }
   } else {

@@ -36,11 +36,11 @@ for it in range(runs):
         done.append(time.perf_counter() - t0)
     job.finish_async()
     dt = time.perf_counter() - t0
-    # what the host fold of an N-GPU job would do with these completion times (0.8 us per task of
+    # what the host fold of an N-GPU job would do with these completion times (0.6 us per task of
     # the whole chunk, in order): time the fold ends after the GPUs' last chunk
     fold_end, prev = 0.0, 0
     for c in range(nchunks):
-        fold_end = max(fold_end, done[c]) + 0.8e-6 * nranks * (int(ends[c]) - prev)
+        fold_end = max(fold_end, done[c]) + 0.6e-6 * nranks * (int(ends[c]) - prev)
         prev = int(ends[c])
     st = job.stats()
     print(f"overlap={os.environ.get('SEQALK_OVERLAP', 'default')} {name} rank 0 of {nranks}, {nchunks} chunks, {len(ids)} tasks: "

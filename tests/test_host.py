@@ -156,19 +156,14 @@ def test_partition_chunks_matches_per_chunk_partition(seqalk):
             assert all(np.array_equal(a, b) for a, b in zip(ref, chunks[c]))
 
 
-def test_chunk_bounds_taper_in_pairs(seqalk):
-    """Chunks complete in pairs on a GPU (two overlapped batch pipelines): equal chunks inside a
-    pair, body pairs of equal size, the last pairs shrink by 0.6 each (csrc/api.cu chunk_bounds)."""
+def test_chunk_bounds_shrink_geometrically(seqalk):
+    """Chunk sizes shrink by 0.8 per chunk (csrc/api.cu chunk_bounds): the results in flight — and the
+    chain fold left when the GPUs finish — shrink with them; small jobs get equal chunks."""
     T = 499500
-    for n in (10, 14, 18):
+    for n in (4, 10, 14):
         b = seqalk.chunk_bounds(T, n)
-        sizes = np.diff(np.asarray(b))
+        sizes = np.diff(np.asarray(b)).astype(float)
         assert b[0] == 0 and b[-1] == T and (sizes > 0).all()
-        pairs = sizes.reshape(-1, 2)
-        assert (np.abs(pairs[:, 0] - pairs[:, 1]) <= 1).all()
-        ps = pairs.sum(axis=1).astype(float)
-        assert np.allclose(ps[-4:] / ps[-5:-1], 0.6, atol=0.01)
-        assert np.allclose(ps[:-4] / ps[0], 1.0, atol=0.01)
-    assert seqalk.chunk_bounds(100, 4) == [0, 25, 50, 75, 100]  # small jobs: equal chunks
-    b = seqalk.chunk_bounds(T, 9)  # odd: the last chunk stands alone
-    assert b[0] == 0 and b[-1] == T and all(x < y for x, y in zip(b, b[1:]))
+        assert np.allclose(sizes[1:] / sizes[:-1], 0.8, atol=0.01)
+    assert sum(np.diff(seqalk.chunk_bounds(T, 14))[-3:]) < 0.05 * T
+    assert seqalk.chunk_bounds(100, 4) == [0, 25, 50, 75, 100]
