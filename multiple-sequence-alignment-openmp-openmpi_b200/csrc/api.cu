@@ -66,6 +66,7 @@ struct Runtime {
   // fused gather: task-ordered result arrays on device 0, kept between calls (allocating and
   // freeing peer-mapped memory inside the call cost up to 0.6 s on some boxes)
   void *pen0 = nullptr, *dig0 = nullptr;
+  uint8_t *dig_host = nullptr;  // page-locked landing buffer of the digests (folded from here)
   size_t res_cap = 0;  // tasks
   // phase times of the last seqalk_all_pairs call (seqalk_profile)
   double prof[SEQALK_PROFILE_LEN] = {0};
@@ -75,6 +76,7 @@ struct Runtime {
     SEQALK_CUDA(cudaSetDevice(0));
     SEQALK_CUDA(cudaMalloc(&pen0, tasks * sizeof(int32_t)));
     SEQALK_CUDA(cudaMalloc(&dig0, tasks * 64));
+    SEQALK_CUDA(cudaMallocHost(reinterpret_cast<void **>(&dig_host), tasks * 64));
     res_cap = tasks;
   }
   void release_results() {
@@ -82,8 +84,10 @@ struct Runtime {
       cudaSetDevice(0);
       cudaFree(pen0);
       cudaFree(dig0);
+      cudaFreeHost(dig_host);
     }
     pen0 = dig0 = nullptr;
+    dig_host = nullptr;
     res_cap = 0;
   }
 };
@@ -282,7 +286,7 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
       throw;
     }
   }
-  std::vector<uint8_t> digests((size_t)T * 64);
+  uint8_t *const digests = r.dig_host;
   size_t hl = 0;
   digest_hex[0] = 0;
   // one folder thread takes the chunks in order as their results reach the host, so that this
@@ -299,7 +303,7 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
         if (ready <= c) return;
       }
       const size_t lo = (size_t)bounds[c], n = (size_t)(bounds[c + 1] - bounds[c]);
-      if (n) fold_chain(digests.data() + 64 * lo, n, digest_hex, &hl);
+      if (n) fold_chain(digests + 64 * lo, n, digest_hex, &hl);
       if (trace) mark("folded chunk", c);
     }
   });
@@ -314,7 +318,7 @@ void all_pairs_peer(Runtime &r, const SeqPack &pack, int k, int pxy, int pgap, i
         const auto t_copy = std::chrono::steady_clock::now();
         SEQALK_CUDA(cudaSetDevice(0));
         SEQALK_CUDA(cudaMemcpy(penalties + lo, pen0 + lo, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        SEQALK_CUDA(cudaMemcpy(digests.data() + 64 * lo, dig0 + 64 * lo, n * 64, cudaMemcpyDeviceToHost));
+        SEQALK_CUDA(cudaMemcpy(digests + 64 * lo, dig0 + 64 * lo, n * 64, cudaMemcpyDeviceToHost));
         r.prof[4] += ms_since(t_copy);
       }
       {
