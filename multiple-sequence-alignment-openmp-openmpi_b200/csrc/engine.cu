@@ -442,7 +442,6 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     uint64_t strips = 0;
     for (const TaskIJ &tk : tasks_) strips += (uint64_t)num_strips(std::max(pack_->len[tk.i], 1), variant_.R);
     few_pairs_ = strips < 2ull * (uint64_t)sm_count_ * 16;
-    if (few_pairs_ && tiles_ && !std::getenv("SEQALK_FILL_R")) variant_.R = 16;
   }
   int64_t maxlen = 1;
   for (const TaskIJ &tk : tasks_) maxlen = std::max<int64_t>(maxlen, std::max(pack_->len[tk.i], pack_->len[tk.j]));
@@ -461,7 +460,10 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   // 16x2-packed fill (fill16.cu): tile mode, cost table, 1024 / 512-row strip pairs (the geometry
   // of the 32-rows-per-lane fill), penalties small enough for 16-bit relative scores
   fill16_shift_ = 0;
-  main_rp_ = 32;  // 2048-row strip pairs (+ 1024 / 512-row tails): less bookkeeping per cell than 1024-row ones
+  // 2048-row strip pairs (+ 1024 / 512-row tails): less bookkeeping per cell than 1024-row ones;
+  // few-pair jobs take 1024-row ones: more strip pairs in flight (big13 fill 46 -> 41 ms against the
+  // 32-bit fill, the lone 200k x 200k pair 26 -> 24 ms; with 2048-row pairs 31 ms)
+  main_rp_ = few_pairs_ ? 16 : 32;
   if (const char *e = std::getenv("SEQALK_FILL16_RP")) main_rp_ = std::atoi(e) == 16 ? 16 : 32;
   if (tiles_ && variant_.mode == MODE_TAB && variant_.R == 32 && mixed_ && codes_.p) {
     fill16_shift_ = fill16_rebase_shift(pxy, pgap, main_rp_);
@@ -472,6 +474,9 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   }
   if (const char *e = std::getenv("SEQALK_FILL16"))
     if (!std::atoi(e)) fill16_shift_ = 0;
+  // few long pairs without the packed fill: the GPU is filled by the strips of the same pair running
+  // as a wavefront, so use thinner strips (more of them) and publish progress more often
+  if (!fill16_shift_ && few_pairs_ && tiles_ && !std::getenv("SEQALK_FILL_R")) variant_.R = 16;
   const int R = variant_.R;
   Batch cur{0, 0, 0, 0, 0, 0, 0};
   std::vector<size_t> ends;
