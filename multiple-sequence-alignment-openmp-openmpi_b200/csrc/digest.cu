@@ -125,9 +125,11 @@ __device__ __forceinline__ uint64_t hex8(uint32_t v) {
   return out;
 }
 
-// <= 64 registers so that a CTA fits into the sliver of the register file the persistent
-// fill kernel leaves free (see fill_blocks_per_sm).
-__global__ void __launch_bounds__(DIGEST_THREADS, 16) digest_kernel(const DigestArgs a) {
+// CAPPED (dirs mode): <= 64 registers (220 bytes of spills) so that a CTA fits into the sliver of
+// the register file the persistent fill kernel leaves free (see fill_blocks_per_sm).  Tile mode:
+// the packed fill owns the whole register file anyway, the digest takes the 91 registers it wants.
+template <bool CAPPED>
+__global__ void __launch_bounds__(DIGEST_THREADS, CAPPED ? 16 : 1) digest_kernel(const DigestArgs a) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t p = tid >> 1, which = tid & 1;
   const bool valid = p < a.npairs;
@@ -206,7 +208,10 @@ cudaError_t launch_digest(const DigestArgs &args, cudaStream_t stream) {
   if (args.npairs == 0) return cudaSuccess;
   const unsigned threads = 2 * args.npairs;
   const unsigned grid = (threads + DIGEST_THREADS - 1) / DIGEST_THREADS;
-  digest_kernel<<<grid, DIGEST_THREADS, 0, stream>>>(args);
+  if (args.small_regs)
+    digest_kernel<true><<<grid, DIGEST_THREADS, 0, stream>>>(args);
+  else
+    digest_kernel<false><<<grid, DIGEST_THREADS, 0, stream>>>(args);
   return cudaGetLastError();
 }
 

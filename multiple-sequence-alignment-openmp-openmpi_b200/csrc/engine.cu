@@ -925,6 +925,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       da.corner_mode = corner_mode;
       da.pgap = pgap_;
       da.check = static_cast<uint32_t *>(check_.p);
+      da.small_regs = tiles_ ? 0 : 1;
       SEQALK_CUDA(launch_digest(da, st));
     }
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 4], st));

@@ -115,6 +115,7 @@ struct DigestArgs {
   int32_t corner_mode;
   int32_t pgap;
   uint32_t *check;
+  int32_t small_regs;           // 1: the 64-register build (dirs mode: runs beside the persistent fill)
 };
 
 // Score-only result: penalties without alignment strings (reference result dp[m][n],
