@@ -125,9 +125,10 @@ __device__ __forceinline__ uint64_t hex8(uint32_t v) {
   return out;
 }
 
-// CAPPED (dirs mode): <= 64 registers (220 bytes of spills) so that a CTA fits into the sliver of
-// the register file the persistent fill kernel leaves free (see fill_blocks_per_sm).  Tile mode:
-// the packed fill owns the whole register file anyway, the digest takes the 91 registers it wants.
+// CAPPED (the default): <= 64 registers (220 bytes of spills) so that a CTA fits into the sliver of
+// the register file the persistent fill kernel leaves free (dirs mode, see fill_blocks_per_sm) and
+// four CTAs fit into what one exiting CTA of the packed fill frees (tile mode, overlapped
+// pipelines).  Uncapped: the 91 registers it wants — faster alone, slower inside the overlapped job.
 template <bool CAPPED>
 __global__ void __launch_bounds__(DIGEST_THREADS, CAPPED ? 16 : 1) digest_kernel(const DigestArgs a) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;

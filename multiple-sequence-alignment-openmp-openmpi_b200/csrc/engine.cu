@@ -925,7 +925,11 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       da.corner_mode = corner_mode;
       da.pgap = pgap_;
       da.check = static_cast<uint32_t *>(check_.p);
-      da.small_regs = tiles_ ? 0 : 1;
+      // the 64-register build: alone it is 12 % slower than the 91-register one (cfg4: 72 vs 63 ms),
+      // but four of its CTAs fit exactly into the registers one exiting fill CTA frees, and the
+      // overlapped job is 1.6 % faster with it (4.70 s vs 4.78 s, same box); SEQALK_DIGEST_CAP=0
+      da.small_regs = 1;
+      if (const char *e = std::getenv("SEQALK_DIGEST_CAP")) da.small_regs = std::atoi(e) ? 1 : 0;
       SEQALK_CUDA(launch_digest(da, st));
     }
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 4], st));
