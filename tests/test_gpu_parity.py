@@ -312,6 +312,10 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     {"SEQALK_FILL_R": "32", "SEQALK_TB_LONG": "0", "SEQALK_DIR_BUDGET_GB": "0.001"},
     {"SEQALK_FILL_R": "32", "SEQALK_TB_LONG": "0", "SEQALK_DIR_BUDGET_GB": "0.001", "SEQALK_SLOTS": "2",
      "SEQALK_POST_PRIORITY": "0"},
+    # 32-bit fill (int32 column checkpoints every 32 macro columns) under the many-pair tracebacks
+    {"SEQALK_FILL16": "0", "SEQALK_TB_LONG": "0"},
+    {"SEQALK_FILL16": "0", "SEQALK_TB_LONG": "0", "SEQALK_TB_HALF": "0"},
+    {"SEQALK_FILL16": "0", "SEQALK_TB_LONG": "0", "SEQALK_FORCE_GENERAL": "1"},
 ], ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
 def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatch, env):
     """Rows per lane (8/16), cost by compare or by 4-letter table, adds on ALU or FMA pipe,
@@ -334,6 +338,13 @@ def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatc
         job.run()
         pen, dig = job.fetch()
     od, op, oh = oracle.all_pairs(genes3, 5, 1, want_pair_hashes=True)
+    assert np.array_equal(pen, op) and [d.tobytes().hex() for d in dig] == oh
+    # a 20-letter alphabet: the compare kernels (no cost table), whatever traceback the env selects
+    genes20 = [bytes(rnd.choice(b"ACDEFGHIKLMNPQRSTVWY") for _ in range(rnd.randint(100, 900))) for _ in range(7)]
+    with seqalk.Job(genes20, 4, 3) as job:
+        job.run()
+        pen, dig = job.fetch()
+    od, op, oh = oracle.all_pairs(genes20, 4, 3, want_pair_hashes=True)
     assert np.array_equal(pen, op) and [d.tobytes().hex() for d in dig] == oh
 
 
