@@ -125,6 +125,23 @@ __device__ __forceinline__ uint64_t hex8(uint32_t v) {
   return out;
 }
 
+// The pair's penalty to its slot of the job-wide array, and the self-check: the fill's own dp[m][n]
+// must equal the cost of the path the traceback walked.
+__device__ __forceinline__ void publish_penalty(const DigestArgs &a, uint32_t p) {
+  const int32_t pen = a.penalties[p];
+  a.penalties_out[a.result_slot[p]] = pen;
+  if (a.corner_mode != CORNER_NONE) {
+    const PairDesc P = a.pairs[p];
+    if (P.m > 0 && P.n > 0) {
+      const int32_t score = a.brow[P.brow_off + corner_index(P, a.corner_mode)] + (P.m + P.n) * a.pgap;
+      if (score != pen) {
+        atomicAdd(a.check, 1u);
+        atomicMin(a.check + 1, (uint32_t)P.task_id);
+      }
+    }
+  }
+}
+
 // CAPPED (the default): <= 64 registers (220 bytes of spills) so that a CTA fits into the sliver of
 // the register file the persistent fill kernel leaves free (dirs mode, see fill_blocks_per_sm) and
 // four CTAs fit into what one exiting CTA of the packed fill frees (tile mode, overlapped
@@ -134,6 +151,10 @@ __global__ void __launch_bounds__(DIGEST_THREADS, CAPPED ? 16 : 1) digest_kernel
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t p = tid >> 1, which = tid & 1;
   const bool valid = p < a.npairs;
+  if (a.host_hash) {  // the digests of this batch were computed by the host (engine.cu): penalties + self-check only
+    if (valid && !which) publish_penalty(a, p);
+    return;
+  }
   Sha512State st;
   st.init();
   if (valid) {
@@ -171,18 +192,7 @@ __global__ void __launch_bounds__(DIGEST_THREADS, CAPPED ? 16 : 1) digest_kernel
   uint64_t *dst = reinterpret_cast<uint64_t *>(a.digests + (uint64_t)a.result_slot[p] * 64);
 #pragma unroll
   for (int k = 0; k < 8; ++k) dst[k] = bswap64(fin.s[k]);
-  const int32_t pen = a.penalties[p];
-  a.penalties_out[a.result_slot[p]] = pen;
-  if (a.corner_mode != CORNER_NONE) {
-    const PairDesc P = a.pairs[p];
-    if (P.m > 0 && P.n > 0) {
-      const int32_t score = a.brow[P.brow_off + corner_index(P, a.corner_mode)] + (P.m + P.n) * a.pgap;
-      if (score != pen) {
-        atomicAdd(a.check, 1u);
-        atomicMin(a.check + 1, (uint32_t)P.task_id);
-      }
-    }
-  }
+  publish_penalty(a, p);
 }
 
 __global__ void __launch_bounds__(128) score_kernel(const ScoreArgs a) {

@@ -3,6 +3,7 @@
 #include "sha512_host.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -263,7 +264,7 @@ DeviceWorker::~DeviceWorker() {
   cudaDeviceSynchronize();
   for (Slot &s : slots_) {
     for (DevBuf *b : {&s.pairs, &s.tasks, &s.slots, &s.progress, &s.brow, &s.dirs, &s.out, &s.align, &s.cost,
-                      &s.counter})
+                      &s.counter, &s.band_tiles, &s.band_tables, &s.band_state, &s.band_visits})
       release(*b);
     if (s.h_stage) cudaFreeHost(s.h_stage);
     if (s.staged) cudaEventDestroy(s.staged);
@@ -283,6 +284,7 @@ DeviceWorker::~DeviceWorker() {
   release(res_dig_);
   release(check_);
   if (h_res_) cudaFreeHost(h_res_);
+  if (h_hash_) cudaFreeHost(h_hash_);
   for (cudaEvent_t e : ev_) cudaEventDestroy(e);
 }
 
@@ -464,7 +466,10 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   // few-pair jobs take 1024-row ones: more strip pairs in flight (big13 fill 46 -> 41 ms against the
   // 32-bit fill, the lone 200k x 200k pair 26 -> 24 ms; with 2048-row pairs 31 ms)
   main_rp_ = few_pairs_ ? 16 : 32;
-  if (const char *e = std::getenv("SEQALK_FILL16_RP")) main_rp_ = std::atoi(e) == 16 ? 16 : 32;
+  if (const char *e = std::getenv("SEQALK_FILL16_RP")) {
+    const int v = std::atoi(e);
+    main_rp_ = (v == 16 || v == 8 || v == 4) ? v : 32;  // 8 / 4: strip pairs of 512 / 256 rows (one-launch kernel only)
+  }
   if (tiles_ && variant_.mode == MODE_TAB && variant_.R == 32 && mixed_ && codes_.p) {
     fill16_shift_ = fill16_rebase_shift(pxy, pgap, main_rp_);
     if (!fill16_shift_ && main_rp_ == 32) {
@@ -752,7 +757,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       const char *e = std::getenv("SEQALK_FILL16_SPLIT");
       return e && std::atoi(e) != 0;
     }();
-    const bool one_launch = fill16_shift_ && !split16;
+    const bool one_launch = fill16_shift_ && (!split16 || main_rp_ <= 8);  // thin strip pairs: the one-launch kernel only
     if (one_launch) {
       // one queue for every strip pair of the batch, critical path first: ordered by the DP cells
       // from the strip pair's first row to the end of its pair (a predecessor has more of them, so
@@ -897,6 +902,53 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     if (const char *e = std::getenv("SEQALK_TB_LONG")) ta.long_pairs = std::atoi(e) ? 1 : 0;
     ta.half_warp = 1;  // two pairs per warp (SEQALK_TB_HALF=0: one warp per pair)
     if (const char *e = std::getenv("SEQALK_TB_HALF")) ta.half_warp = std::atoi(e) ? 1 : 0;
+    // 256-row strip pairs: the 8 rows of a half-warp lane would span two virtual lanes of the fill
+    // (two re-base histories); the whole-warp tracebacks read 4 rows per lane
+    if (fill16_shift_ && main_rp_ == 4) ta.half_warp = 0;
+    // a few LONG pairs: banded traceback in chapters (traceback_tiles.cu) — all tiles near the path
+    // recomputed at once, one warp each, instead of one after the other (the 200k x 200k pair:
+    // 38 ms -> see profiles/).  SEQALK_TB_BAND=0 / 1 forces it off / on (tests run it on small inputs),
+    // SEQALK_TB_BAND_LEVELS / SEQALK_TB_BAND_HALFWIDTH set the chapter length and the band.
+    ta.band = 0;
+    ta.band_levels = ta.band_halfwidth = ta.band_chapters = ta.band_visit_cap = 0;
+    ta.band_tiles = nullptr;
+    ta.band_tables = nullptr;
+    ta.band_state = nullptr;
+    ta.band_visits = nullptr;
+    if (tiles_ && !fill_only) {
+      int64_t longest = 0;
+      int max_level = 0;
+      for (size_t p = 0; p < B.count; ++p) {
+        longest = std::max<int64_t>(longest, (int64_t)hp[p].m + hp[p].n);
+        if (hp[p].m > 0 && hp[p].n > 0)
+          max_level = std::max(max_level, (hp[p].m - 1) / TILE_ROWS + (hp[p].n - 1) / (4 * CKQ));
+      }
+      bool band = ta.long_pairs && B.count <= 512 && longest >= 32768;
+      if (const char *e = std::getenv("SEQALK_TB_BAND")) band = std::atoi(e) != 0 && B.count <= 4096;
+      if (band) {
+        ta.band = 1;
+        ta.band_levels = 63;
+        ta.band_halfwidth = B.count <= 8 ? 4 : 2;
+        if (const char *e = std::getenv("SEQALK_TB_BAND_LEVELS")) ta.band_levels = std::max(0, std::min(1023, std::atoi(e)));
+        if (const char *e = std::getenv("SEQALK_TB_BAND_HALFWIDTH")) ta.band_halfwidth = std::max(0, std::min(16, std::atoi(e)));
+        // chapters: what a path that stays inside its bands needs, plus a quarter for chapters cut
+        // short by a turn of the path; the last one finishes whatever is left
+        const int nominal = max_level / (ta.band_levels + 1) + 1;
+        ta.band_chapters = nominal + nominal / 4 + 4;
+        if (const char *e = std::getenv("SEQALK_TB_BAND_CHAPTERS")) ta.band_chapters = std::max(1, std::atoi(e));
+        ta.band_visit_cap = ta.band_levels + 2;
+        const size_t images = (size_t)(ta.band_levels + 1) * (size_t)(2 * ta.band_halfwidth + 1);
+        ensure(G.band_tiles, B.count * images * (size_t)(CKQ * TILE_ROWS));
+        ensure(G.band_tables, B.count * images * (size_t)(TILE_ROWS + 4 * CKQ) * sizeof(uint32_t));
+        ensure(G.band_state, B.count * sizeof(BandState));
+        ensure(G.band_visits, B.count * (size_t)ta.band_visit_cap * sizeof(BandVisit));
+        ta.band_tiles = static_cast<uint8_t *>(G.band_tiles.p);
+        ta.band_tables = static_cast<uint32_t *>(G.band_tables.p);
+        ta.band_state = static_cast<BandState *>(G.band_state.p);
+        ta.band_visits = static_cast<BandVisit *>(G.band_visits.p);
+        stats_.traceback_launches += 3 * (uint32_t)ta.band_chapters;  // + the finish launch, counted below
+      }
+    }
     if (!fill_only) SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));
 
@@ -930,6 +982,29 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       // overlapped job is 1.6 % faster with it (4.70 s vs 4.78 s, same box); SEQALK_DIGEST_CAP=0
       da.small_regs = 1;
       if (const char *e = std::getenv("SEQALK_DIGEST_CAP")) da.small_regs = std::atoi(e) ? 1 : 0;
+      // A few very long strings: SHA-512 is serial per string, and one GPU lane hashes ~27 MB/s
+      // against ~260 MB/s of a host core (the 200k x 200k pair: 15 ms on the GPU).  Such a batch's
+      // strings are brought to the host, hashed there by a few threads and the 64-byte digests
+      // uploaded; the kernel then only publishes the penalties and runs the self-check.
+      // SEQALK_HOST_HASH=0 / 1 forces it off / on.
+      da.host_hash = 0;
+      {
+        uint64_t longest = 0, total = 0;
+        for (size_t p = 0; p < B.count; ++p) {
+          const uint64_t len = (uint64_t)hp[p].m + (uint64_t)hp[p].n;
+          longest = std::max(longest, len);
+          total += 2 * len;
+        }
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const double threads = (double)std::min<uint64_t>(std::min<uint64_t>(hw, 16), 2 * B.count);
+        const double device_ns = 37.5 * (double)longest, host_ns = 4.0 * (double)total / threads + 100e3;
+        bool host = few_pairs_ && B.count > 0 && 2.0 * host_ns < device_ns;
+        if (const char *e = std::getenv("SEQALK_HOST_HASH")) host = std::atoi(e) != 0 && B.count > 0;
+        if (host) {
+          host_hash_batch(S, G, B.count, B.out_bytes, digests_dev, hs, st);
+          da.host_hash = 1;
+        }
+      }
       SEQALK_CUDA(launch_digest(da, st));
     }
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 4], st));
@@ -981,6 +1056,54 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   }
   stats_.wall_ms +=
       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+}
+
+// Host side of the per-pair hash for a batch of a few very long pairs (same result as
+// digest_kernel: problemhash = H(hex(H(align1)) ++ hex(H(align2))), submit/xuliny-seqalkway.cpp:217-219).
+// Runs on the batch's post stream after the traceback: strings + records to the host, hash, digests
+// back to the slots of the job-wide array (which may live on a peer GPU).
+void DeviceWorker::host_hash_batch(const Slot &S, const Slot &G, size_t count, size_t out_bytes, uint8_t *digests_dev,
+                                   const uint32_t *slots_host, cudaStream_t st) {
+  const size_t rec_off = round_up(out_bytes, 64), dig_off = rec_off + round_up(count * sizeof(PairAlign), 64);
+  const size_t want = dig_off + count * 64;
+  if (want > h_hash_cap_) {
+    if (h_hash_) SEQALK_CUDA(cudaFreeHost(h_hash_));
+    h_hash_ = nullptr;
+    h_hash_cap_ = 0;
+    SEQALK_CUDA(cudaMallocHost(&h_hash_, want + want / 8));
+    h_hash_cap_ = want + want / 8;
+  }
+  uint8_t *h = static_cast<uint8_t *>(h_hash_);
+  SEQALK_CUDA(cudaMemcpyAsync(h, G.out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  SEQALK_CUDA(cudaMemcpyAsync(h + rec_off, G.align.p, count * sizeof(PairAlign), cudaMemcpyDeviceToHost, st));
+  SEQALK_CUDA(cudaStreamSynchronize(st));
+  const PairAlign *rec = reinterpret_cast<const PairAlign *>(h + rec_off);
+  const std::vector<PairDesc> &pairs = S.last_pairs;
+  // one job per string, handed out longest first (the pairs of a batch are laid out longest first)
+  std::vector<char> hex(count * 256);
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const size_t job = next.fetch_add(1);
+      if (job >= 2 * count) break;
+      const size_t p = job >> 1, which = job & 1;
+      const PairDesc &P = pairs[p];
+      char out[129];
+      Sha512::hex(h + P.out_off + which * (size_t)P.cap + rec[p].start, rec[p].len, out);
+      std::memcpy(&hex[p * 256 + which * 128], out, 128);
+    }
+  };
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t nthreads = std::min<size_t>(std::min<size_t>(hw, 16), 2 * count);
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < nthreads; ++t) pool.emplace_back(work);
+  work();
+  for (std::thread &t : pool) t.join();
+  for (size_t p = 0; p < count; ++p) Sha512::raw(&hex[p * 256], 256, h + dig_off + 64 * p);
+  for (size_t p = 0; p < count; ++p)
+    SEQALK_CUDA(cudaMemcpyAsync(digests_dev + 64ull * slots_host[p], h + dig_off + 64 * p, 64, cudaMemcpyDefault, st));
+  // the landing buffer is reused by the next batch
+  SEQALK_CUDA(cudaStreamSynchronize(st));
 }
 
 void DeviceWorker::start_async(int32_t *penalties_dev, uint8_t *digests_dev) {

@@ -130,6 +130,7 @@ class DeviceWorker {
     cudaEvent_t post_done = nullptr;   // traceback + digest (+ D2H) of that batch finished
     bool post_pending = false;
     DevBuf pairs, tasks, slots, progress, brow, dirs, out, align, cost, counter;
+    DevBuf band_tiles, band_tables, band_state, band_visits;  // banded traceback of long pairs (traceback_tiles.cu)
     void *h_stage = nullptr;  // pinned staging: pairs | tasks | slots
     size_t h_cap = 0;
     cudaEvent_t staged = nullptr;  // H2D of the staging buffer finished
@@ -166,6 +167,7 @@ class DeviceWorker {
   bool mixed_ = false;  // tile mode, R = 32: half-height last strips (second fill launch)
   int main_rp_ = 16;      // packed fill: rows per half lane of the main strip pairs (32: 2048-row strip pairs + 1024 / 512-row tails)
   StripGeom geometry(int m) const {
+    if (fill16_shift_ && main_rp_ <= 8) return strip_geometry(m, 2 * main_rp_, false);  // uniform strip pairs of 64 * main_rp_ rows
     return (fill16_shift_ && main_rp_ == 32) ? strip_geometry3(m) : strip_geometry(m, variant_.R, mixed_);
   }
   int fill16_shift_ = 0;  // > 0: the 16x2-packed fill (fill16.cu) runs the tile-mode fill; value = log2 of its re-base interval
@@ -194,6 +196,10 @@ class DeviceWorker {
   std::string async_error_;
   void *h_res_ = nullptr;  // pinned host mirror of the result arrays: T*4 | T*64
   size_t h_res_cap_ = 0;
+  void *h_hash_ = nullptr;  // pinned landing buffer of a batch's alignment strings + records (host hashing)
+  size_t h_hash_cap_ = 0;
+  void host_hash_batch(const Slot &S, const Slot &G, size_t count, size_t out_bytes, uint8_t *digests_dev,
+                       const uint32_t *slots_host, cudaStream_t st);
   std::vector<cudaEvent_t> ev_;
   JobStats stats_;
 };

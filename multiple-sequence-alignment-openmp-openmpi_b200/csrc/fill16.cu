@@ -134,7 +134,7 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
   {
     const uint8_t *__restrict__ xs = a.codes + P.x_off;  // zero padded far beyond m (engine.cu)
     unsigned wa[RP / 4], wb[RP / 4];
-    static_assert(RP == 32 || RP == 16 || RP == 8, "rows per half lane");
+    static_assert(RP == 32 || RP == 16 || RP == 8 || RP == 4, "rows per half lane");
     if constexpr (RP == 32) {
 #pragma unroll
       for (int q4 = 0; q4 < 2; ++q4) {
@@ -148,11 +148,14 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
       const uint4 vb = rowB0 < m ? __ldg(reinterpret_cast<const uint4 *>(xs + rowB0)) : make_uint4(0, 0, 0, 0);
       wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
       wb[0] = vb.x; wb[1] = vb.y; wb[2] = vb.z; wb[3] = vb.w;
-    } else {
+    } else if constexpr (RP == 8) {
       const uint2 va = rowA0 < m ? __ldg(reinterpret_cast<const uint2 *>(xs + rowA0)) : make_uint2(0, 0);
       const uint2 vb = rowB0 < m ? __ldg(reinterpret_cast<const uint2 *>(xs + rowB0)) : make_uint2(0, 0);
       wa[0] = va.x; wa[1] = va.y;
       wb[0] = vb.x; wb[1] = vb.y;
+    } else {
+      wa[0] = rowA0 < m ? __ldg(reinterpret_cast<const unsigned *>(xs + rowA0)) : 0u;
+      wb[0] = rowB0 < m ? __ldg(reinterpret_cast<const unsigned *>(xs + rowB0)) : 0u;
     }
 #pragma unroll
     for (int r = 0; r < RP; ++r) {
@@ -305,7 +308,9 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
           store = ckcol >= 1 && (qcA + 1 < nq || (ckcol >= 2 && qcA - 31 < nq));
           dst = ck + (int64_t)(ckcol - 1) * (int64_t)halfwords;
         }
-        if (store) {
+        if (store && RP == 4) {
+          asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        } else if (store) {
 #pragma unroll
           for (int r8 = 0; r8 < RP / 8; ++r8)
             asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * r8), "r"(h[8 * r8]),
@@ -407,6 +412,9 @@ typedef void (*Fill16Ptr)(const FillArgs);
 Fill16Ptr pick16_all(int rp, int minb) {
   if (rp == 32) return minb == 3 ? fill16_all_kernel<32, 3> : fill16_all_kernel<32, 4>;
   if (rp == 16) return minb == 5 ? fill16_all_kernel<16, 5> : fill16_all_kernel<16, 6>;
+  // thin strip pairs (512 / 256 rows) for jobs of a few long pairs: more warps along the wavefront
+  if (rp == 8) return fill16_all_kernel<8, 8>;
+  if (rp == 4) return fill16_all_kernel<4, 8>;
   return nullptr;
 }
 Fill16Ptr pick16(int rp, int minb) {

@@ -66,6 +66,27 @@ struct FillArgs {
   int32_t main_rp;          // rows per half lane of the job's main strip pairs (16: 1024-row, 32: 2048-row strip pairs)
 };
 
+// Banded traceback of long pairs (traceback_tiles.cu): what a pair carries from one chapter
+// (produce + hop + emit launches) to the next.
+struct BandState {
+  int32_t i, j;       // the path continues from DP cell (i, j)
+  int32_t pos;        // characters [pos, m + n) of the alignment buffers are accounted for
+  int32_t done;       // 1: the path has reached row 0 or column 0
+  int32_t misses;     // tiles the hopping warp had to recompute and walk itself, diagnostics
+  int32_t dhs, dcb;   // tile rows / tile columns the previous chapter moved: slope of the next band
+  int32_t nvisits;    // tiles recorded for this chapter's emit launch
+  int32_t cost_emit;  // path cost collected by the emit launches
+  int32_t pad[7];
+  int32_t cost[32];   // per-lane shares of the path cost collected by the hopping warp
+};
+// A tile the path visits inside the band: what the emit launch needs to walk it.
+struct BandVisit {
+  int32_t hs, cb;  // tile
+  int32_t cell;    // entry cell inside the tile: row | column << 16
+  int32_t pos;     // characters of this tile end at `pos` of the alignment buffers
+  int32_t slot;    // image of the tile
+};
+
 struct TracebackArgs {
   const uint8_t *seq;
   const uint8_t *codes;     // letters remapped to 0..3 (tile mode with MODE_TAB), else null
@@ -89,6 +110,16 @@ struct TracebackArgs {
   int32_t strip_scan;       // 1: the input contains '_' (the gap character): apply the reference's
                             // strip rule literally (submit/xuliny-seqalkway.cpp:191-202): the alignment
                             // starts after the LAST column holding '_' in both strings
+  // tile mode, jobs of a few LONG pairs: banded traceback in chapters (traceback_tiles.cu)
+  int32_t band;             // 1: on
+  int32_t band_levels;      // tile anti-diagonals (levels hs + cb) per chapter after the chapter's first
+  int32_t band_halfwidth;   // tiles recomputed per level = 2 * band_halfwidth + 1
+  int32_t band_chapters;    // chapters enqueued (the last one finishes whatever is left)
+  int32_t band_visit_cap;   // visits a pair can record per chapter
+  uint8_t *band_tiles;      // per pair (band_levels + 1) * (2 * band_halfwidth + 1) direction images of 4 KB
+  uint32_t *band_tables;    // ... and as many transfer tables of 256 words
+  BandState *band_state;    // per pair
+  BandVisit *band_visits;   // per pair band_visit_cap records
 };
 
 // Where the fill left H'[m][n] of a pair (MODE_TAB only: padded rows copy DP row m, so the bottom
@@ -116,6 +147,9 @@ struct DigestArgs {
   int32_t pgap;
   uint32_t *check;
   int32_t small_regs;           // 1: the 64-register build (dirs mode: runs beside the persistent fill)
+  int32_t host_hash;            // 1: the host hashed this batch's strings and uploaded the digests (a few very
+                                // long strings: one SHA-512 lane is ~10x slower than a host core); the kernel
+                                // only publishes the penalties and runs the self-check
 };
 
 // Score-only result: penalties without alignment strings (reference result dp[m][n],

@@ -83,6 +83,101 @@ constexpr int tile_smem_bytes(bool stage) { return TILE_DIR_BYTES + TILE_CHAR_BY
 #define SEQALK_TB_STAGE 1
 #endif
 
+// Stages the tile's characters behind its direction codes (rows / columns past the ends are never
+// walked): LN lanes, lane t brings the RT characters of its rows and 8 characters of y per round.
+template <int RT, int LN>
+__device__ __forceinline__ void stage_tile_chars(const TileCtx &T, int row0, int col0, uint8_t *tile, int lane) {
+  const int r0 = row0 + lane * RT;
+  if (RT == 8)
+    reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES)[lane] =
+        r0 < T.m ? *reinterpret_cast<const uint64_t *>(T.xs + r0) : 0ull;
+  else
+    reinterpret_cast<uint32_t *>(tile + TILE_DIR_BYTES)[lane] =
+        r0 < T.m ? *reinterpret_cast<const uint32_t *>(T.xs + r0) : 0u;
+#pragma unroll
+  for (int c = lane * 8; c < 4 * CKQ; c += 8 * LN)  // 8 y characters per lane and round
+    *reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES + TILE_ROWS + c) =
+        col0 + c < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + col0 + c) : 0ull;
+}
+
+// macro_step (fill_core.cuh, EMIT = true) plus the tile's TRANSFER FUNCTION: next to H' every cell
+// carries E = (exit << 16 | steps): where the traceback path through this cell leaves the tile and
+// how many cells of the tile it visits on the way, E(cell) = E(predecessor of the cell) + 1 — the
+// predecessor chosen exactly as walk_tile reads the 2-bit code (0, 1: diagonal; 2: up; 3: left).
+// Cells outside the tile carry their own exit code and 0 steps: exit = c + 1 for the row above the
+// tile at tile column c (c = -1: the corner), exit = 129 + r for the column left of it at tile row r.
+// Same arithmetic as macro_step, statement by statement (the direction bits must be identical).
+template <int R, int MODE, int ADDMODE>
+__device__ __forceinline__ void macro_step_track(int (&h)[R], int &dg, const int (&xc)[R], const int (&up_in)[4],
+                                                 unsigned yword, int A, int B, int (&outv)[4], unsigned (&bits)[R / 4],
+                                                 int (&eh)[R], int &edg, const int (&eup_in)[4], int (&eout)[4]) {
+  static_assert(ADDMODE != 1, "the traceback runs the plain or the IDP.4A adds");
+#pragma unroll
+  for (int w = 0; w < R / 4; ++w) bits[w] = 0u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    int yc = 0;
+    unsigned sel = 0;
+    if (MODE == MODE_TAB && ADDMODE == 2) {
+      sel = __funnelshift_l(0u, 1u, yword >> (8 * c));
+    } else {
+      yc = (int)((yword >> (8 * c)) & 0xffu);
+      if (MODE == MODE_TAB) sel = (unsigned)(yc >> 3) * 0x1111u + 0x8880u;
+    }
+    int diag = dg, up = up_in[c];
+    dg = up;
+    int ediag = edg, eup = eup_in[c];
+    edg = eup;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int w = (c * R + r) / CELLS_PER_WORD;
+      const int left = h[r], eleft = eh[r];
+      int v;
+      bool not_diag, left_better;
+      if (MODE == MODE_GENERAL) {
+        const bool match = (xc[r] == yc);
+        const int t = diag + B;
+        const int m1 = min(up, left);
+        v = match ? diag + A : min(t, m1);
+        not_diag = (!match) && (t > m1);
+        left_better = up > left;
+        bits[w] = (bits[w] << 2) | (not_diag ? 2u : 0u) | (left_better ? 1u : 0u);
+      } else {
+        int t;
+        if (MODE == MODE_TAB && ADDMODE == 2) {
+          t = __dp4a(xc[r], (int)sel, diag);
+        } else if (MODE == MODE_TAB) {
+          int cost;
+          asm("prmt.b32 %0, %1, %2, %3;" : "=r"(cost) : "r"(xc[r]), "r"(0), "r"(sel));
+          t = diag + cost;
+        } else {
+          t = diag + B;
+          asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p add.s32 %0, %3, %4;}" : "+r"(t) : "r"(xc[r]), "r"(yc), "r"(diag), "r"(A));
+        }
+        v = min(min(up, left), t);
+        const int d1 = v - t, d2 = left - up;
+        bits[w] = __funnelshift_l((unsigned)d1, bits[w], 1);
+        bits[w] = __funnelshift_l((unsigned)d2, bits[w], 1);
+        not_diag = d1 < 0;
+        left_better = d2 < 0;
+      }
+      const int e = (not_diag ? (left_better ? eleft : eup) : ediag) + 1;
+      diag = left;
+      up = v;
+      h[r] = v;
+      ediag = eleft;
+      eup = e;
+      eh[r] = e;
+    }
+    outv[c] = up;
+    eout[c] = eup;
+  }
+}
+
+// Entries of a tile's transfer table (256 words): the cells through which a path can enter the tile —
+// bottom row (index = tile column) and right column (index = 128 + tile row).
+constexpr int TILE_TABLE_WORDS = TILE_ROWS + 4 * CKQ;
+
 // Recomputes the directions of tile (hs, cb), macro columns [0, tq) and lanes [0, tmax], into
 // `tile`, by a group of LN lanes owning RT rows each (`lane` = index inside the group; every lane of
 // the WARP must call this together, with the same `nsteps` >= tq + tmax: the groups of a warp run
@@ -92,9 +187,11 @@ constexpr int tile_smem_bytes(bool stage) { return TILE_DIR_BYTES + TILE_CHAR_BY
 // STAGE: the group first copies the top edge to shared memory with a few wide loads; otherwise
 // lane 0 fetches it from global memory one macro column ahead, which exposes the load latency on
 // every step unless other warps cover it.
-template <int MODE, int ADDMODE, bool STAGE, int RT, int LN = TILE_ROWS / RT>
+// TRACK: also writes the tile's transfer table (macro_step_track) to `table`: E of the bottom row's cells
+// (full-height tiles) and of the right column's cells (full-width tiles).
+template <int MODE, int ADDMODE, bool STAGE, int RT, int LN = TILE_ROWS / RT, bool TRACK = false>
 __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb, int tq, int tmax, int nsteps,
-                                               uint8_t *tile, int lane) {
+                                               uint8_t *tile, int lane, uint32_t *table = nullptr) {
   static_assert(LN * RT <= TILE_ROWS, "LN lanes x RT rows: the tile, or (LN * RT < TILE_ROWS) its upper part");
   constexpr int WPE = RT / 4;         // 32-bit words of direction codes per lane and macro column
   static_assert(RT == 8 || RT == 4, "rows per lane");
@@ -164,22 +261,18 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
       for (int r = 0; r < RT; ++r) h[r] = 0;
     }
   }
-  if (tq > 0) {  // stage the tile's characters (rows / columns past the ends are never walked)
-    const int r0 = row0 + lane * RT;
-    if (RT == 8)
-      reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES)[lane] =
-          r0 < T.m ? *reinterpret_cast<const uint64_t *>(T.xs + r0) : 0ull;
-    else
-      reinterpret_cast<uint32_t *>(tile + TILE_DIR_BYTES)[lane] =
-          r0 < T.m ? *reinterpret_cast<const uint32_t *>(T.xs + r0) : 0u;
-#pragma unroll
-    for (int c = lane * 8; c < 4 * CKQ; c += 8 * LN)  // 8 y characters per lane and round
-      *reinterpret_cast<uint64_t *>(tile + TILE_DIR_BYTES + TILE_ROWS + c) =
-          col0 + c < T.n ? *reinterpret_cast<const uint64_t *>(T.ys + col0 + c) : 0ull;
-  }
+  if (tq > 0) stage_tile_chars<RT, LN>(T, row0, col0, tile, lane);
   const int32_t *toprow = hs > 0 ? T.brow + (uint64_t)(hs - 1) * T.bstride : nullptr;
   int dg = __shfl_up_sync(FULL, h[RT - 1], 1, LN);
   if (lane == 0) dg = (toprow && cb > 0) ? __ldcg(toprow + col0 - 1) : 0;
+  int eh[RT], edg = 0, eout[4] = {0, 0, 0, 0};
+  if (TRACK) {
+    static_assert(!TRACK || LN * RT == TILE_ROWS, "transfer tables: whole tiles");
+#pragma unroll
+    for (int r = 0; r < RT; ++r) eh[r] = (4 * CKQ + 1 + lane * RT + r) << 16;  // left of the tile: exit through the left edge at this row
+    edg = __shfl_up_sync(FULL, eh[RT - 1], 1, LN);
+    if (lane == 0) edg = 0;  // the corner
+  }
   int outv[4] = {0, 0, 0, 0};
   unsigned yw = 0;
   int4 top = make_int4(0, 0, 0, 0);
@@ -218,15 +311,33 @@ __device__ __forceinline__ void recompute_tile(const TileCtx &T, int hs, int cb,
       }
     }
     const int qc = q - lane;
+    int eup_in[4] = {0, 0, 0, 0};
+    if (TRACK) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) eup_in[c] = __shfl_up_sync(FULL, eout[c], 1, LN);
+      if (lane == 0) {  // above the tile: exit through the top edge at this column
+#pragma unroll
+        for (int c = 0; c < 4; ++c) eup_in[c] = (4 * q + c + 1) << 16;
+      }
+    }
     if (qc >= 0 && qc < tq && lane <= tmax) {
       yw = ny;
       unsigned bits[RT / 4];
-      macro_step<RT, MODE, ADDMODE, true>(h, dg, xc, up_in, yw, T.A, T.B, 1, -1, outv, bits);
+      if (TRACK) {
+        macro_step_track<RT, MODE, ADDMODE>(h, dg, xc, up_in, yw, T.A, T.B, outv, bits, eh, edg, eup_in, eout);
+        if (lane == LN - 1) reinterpret_cast<int4 *>(table)[qc] = make_int4(eout[0], eout[1], eout[2], eout[3]);
+      } else {
+        macro_step<RT, MODE, ADDMODE, true>(h, dg, xc, up_in, yw, T.A, T.B, 1, -1, outv, bits);
+      }
       if (RT == 8)
         reinterpret_cast<uint2 *>(sdirs)[qc * LN + lane] = make_uint2(bits[0], bits[WPE - 1]);
       else
         sdirs[qc * LN + lane] = bits[0];
     }
+  }
+  if (TRACK && tq == CKQ && lane <= tmax) {
+    static_assert(!TRACK || RT == 4, "one int4 of right-column entries per lane");
+    reinterpret_cast<int4 *>(table + 4 * CKQ)[lane] = make_int4(eh[0], eh[1], eh[2], eh[3]);
   }
 }
 
@@ -515,8 +626,246 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
   if (warp == 0) finish_pair<32>(a, T, p, s_i, s_j, W, lane, 0xffffffffu, 0);
 }
 
+// ---- Banded traceback in chapters (jobs of a few LONG pairs).
+//
+// The four-warp kernel above is a serial chain of tile recomputes: ~12 us per tile on a lone warp
+// (63 dependent macro steps), ~3 100 tiles for a 200k x 200k pair, and even with the tiles at hand the
+// walk itself costs ~45 ns per step on a lone warp.  Neither the recompute of a tile nor the walk
+// inside it depends on the rest of the path — only WHERE the path enters the tile does.  So the
+// traceback runs in CHAPTERS of up to band_levels + 1 tile anti-diagonals (levels hs + cb), three
+// launches each:
+//   PRODUCE  one warp per tile, all tiles at once: every tile within band_halfwidth of the line the
+//            path is expected to follow is recomputed; its 4 KB direction image and its transfer table
+//            (entry cell on the bottom row / right column -> exit cell + steps, macro_step_track) go to HBM;
+//   HOP      one warp per pair, serial but short: from the chapter's first cell the path is followed
+//            tile by tile with ONE table look-up per tile, which yields every visited tile's entry cell
+//            and the position of its characters in the alignment strings;
+//   EMIT     one warp per visited tile, all at once: copies the image to shared memory, walks the tile
+//            from its entry cell and writes the characters (walk_tile, as in every other kernel).
+// The band follows the path: a chapter is centred on the line through its first tile with the slope of
+// the previous chapter's displacement (the first: towards DP cell (0, 0)); when the path leaves the band
+// the chapter ends there and the next one is re-centred (paths of unequal-length pairs are long
+// straight stretches — diagonal runs and gap runs — with few turns).  A tile that still is not covered
+// (a pair's first tile, entered in its interior; everything in the last chapter the host enqueued) is
+// recomputed and walked by the hopping warp itself (BandState::misses), so the result never depends
+// on the band.  A FINISH launch writes the tails and the result records.
+struct BandGeom {
+  int hs0, cb0, L0, W1;
+  long long num, den;  // slope of the centre line: tile rows per level = num / den
+};
+__device__ __forceinline__ BandGeom band_geom(const TracebackArgs &a, int i0, int j0, int dhs, int dcb) {
+  BandGeom g;
+  g.hs0 = (i0 - 1) / TILE_ROWS;
+  g.cb0 = (j0 - 1) / (4 * CKQ);
+  g.L0 = g.hs0 + g.cb0;
+  g.W1 = 2 * a.band_halfwidth + 1;
+  if (dhs + dcb > 0) {  // the previous chapter's displacement
+    g.num = dhs;
+    g.den = dhs + dcb;
+  } else {  // towards DP cell (0, 0)
+    g.num = i0;
+    g.den = (long long)i0 + j0;
+  }
+  return g;
+}
+// tile row of the band's centre, d levels below the chapter's first tile
+__device__ __forceinline__ int band_center(const BandGeom &g, int d) {
+  return g.hs0 - (int)(((long long)d * g.num + (g.den >> 1)) / g.den);
+}
+// index of tile (hs, cb) among the chapter's images, -1: not part of the band
+__device__ __forceinline__ int band_slot(const TracebackArgs &a, const BandGeom &g, int hs, int cb) {
+  const int d = g.L0 - (hs + cb);
+  if (hs < 0 || cb < 0 || hs > g.hs0 || cb > g.cb0 || d < 0 || d > a.band_levels) return -1;
+  const int k = hs - band_center(g, d) + a.band_halfwidth;
+  if (k < 0 || k >= g.W1) return -1;
+  return d * g.W1 + k;
+}
+// a pair's state at the start of chapter `chapter`
+struct BandStart {
+  int i, j, dhs, dcb;
+};
+__device__ __forceinline__ BandStart band_start(const TracebackArgs &a, const PairDesc &P, uint32_t p, int chapter) {
+  BandStart b{P.m, P.n, 0, 0};
+  if (chapter > 0) {
+    const BandState *S = a.band_state + p;
+    b.i = S->done ? 0 : S->i;
+    b.j = S->done ? 0 : S->j;
+    b.dhs = S->dhs;
+    b.dcb = S->dcb;
+  }
+  return b;
+}
+__device__ __forceinline__ int band_images(const TracebackArgs &a) { return (a.band_levels + 1) * (2 * a.band_halfwidth + 1); }
+__device__ __forceinline__ const uint8_t *band_image(const TracebackArgs &a, uint32_t p, int slot) {
+  return a.band_tiles + ((uint64_t)p * (uint64_t)band_images(a) + (uint64_t)slot) * TILE_DIR_BYTES;
+}
+__device__ __forceinline__ uint32_t *band_table(const TracebackArgs &a, uint32_t p, int slot) {
+  return a.band_tables + ((uint64_t)p * (uint64_t)band_images(a) + (uint64_t)slot) * TILE_TABLE_WORDS;
+}
+
+constexpr int BAND_WARPS = 4;  // warps per CTA of the produce and emit kernels
+template <int MODE, int ADDMODE>
+__global__ void __launch_bounds__(32 * BAND_WARPS) traceback_band_produce_kernel(const TracebackArgs a, const int chapter) {
+  constexpr int RT = RT_WARP;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t p = blockIdx.y;
+  const PairDesc P = a.pairs[p];
+  const BandStart b = band_start(a, P, p, chapter);
+  if (b.i <= 0 || b.j <= 0) return;  // finished (or nothing to walk)
+  const BandGeom g = band_geom(a, b.i, b.j, b.dhs, b.dcb);
+  const int slot = (int)blockIdx.x * BAND_WARPS + warp;
+  if (slot >= band_images(a)) return;
+  const int d = slot / g.W1, k = slot - d * g.W1;
+  const int hs = band_center(g, d) + k - a.band_halfwidth, cb = g.L0 - d - hs;
+  if (hs < 0 || cb < 0 || hs > g.hs0 || cb > g.cb0) return;
+  const TileCtx T = make_ctx<MODE>(a, P);
+  uint8_t *tile = smem + (size_t)warp * LONG_TILE_BYTES;
+  const int tq = min(CKQ, T.nq - cb * CKQ), tmax = min(31, (T.m - 1 - hs * TILE_ROWS) / RT);
+  recompute_tile<MODE, ADDMODE, true, RT, TILE_ROWS / RT, true>(T, hs, cb, tq, tmax, tq + tmax, tile, lane,
+                                                                band_table(a, p, slot));
+  __syncwarp();
+  uint4 *dst = reinterpret_cast<uint4 *>(const_cast<uint8_t *>(band_image(a, p, slot)));
+  const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+#pragma unroll
+  for (int r = 0; r < TILE_DIR_BYTES / 16 / 32; ++r) dst[lane + 32 * r] = src[lane + 32 * r];
+}
+
+template <int MODE, int ADDMODE>
+__global__ void __launch_bounds__(32) traceback_band_hop_kernel(const TracebackArgs a, const int chapter, const int last) {
+  constexpr int RT = RT_WARP;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x;
+  const uint32_t p = blockIdx.x;
+  BandState *S = a.band_state + p;
+  if (chapter > 0 && S->done) {
+    if (lane == 0) S->nvisits = 0;  // nothing left for the emit launches
+    return;
+  }
+  const PairDesc P = a.pairs[p];
+  const TileCtx T = make_ctx<MODE>(a, P);
+  const BandStart b = band_start(a, P, p, chapter);
+  PathOut W{a.out + P.out_off, a.out + P.out_off + P.cap, T.m + T.n, 0};
+  int i = b.i, j = b.j, misses = 0;
+  if (chapter > 0) {
+    W.pos = S->pos;
+    W.cost = S->cost[lane];
+    misses = S->misses;
+  }
+  const BandGeom g = band_geom(a, max(i, 1), max(j, 1), b.dhs, b.dcb);
+  const int lowest = g.L0 - a.band_levels;  // last level of this chapter's band
+  BandVisit *list = a.band_visits + (uint64_t)p * (uint64_t)a.band_visit_cap;
+  int nlist = 0, ntiles = 0;
+  while (i > 0 && j > 0) {
+    const int hs = (i - 1) / TILE_ROWS, cb = (j - 1) / (4 * CKQ);
+    if (!last && hs + cb < lowest) break;
+    const int row0 = hs * TILE_ROWS, col0 = cb * 4 * CKQ;
+    const int li = i - 1 - row0, lj = j - 1 - col0;
+    const int entry = li == TILE_ROWS - 1 ? lj : (lj == 4 * CKQ - 1 ? 4 * CKQ + li : -1);
+    const int slot = entry >= 0 ? band_slot(a, g, hs, cb) : -1;
+    if (slot >= 0 && nlist < a.band_visit_cap) {
+      const uint32_t E = __ldcg(band_table(a, p, slot) + entry);
+      if (lane == 0) list[nlist] = BandVisit{hs, cb, li | (lj << 16), W.pos, slot};
+      ++nlist;
+      const int steps = (int)(E & 0xffffu), code = (int)(E >> 16);
+      W.pos -= steps;
+      if (code <= 4 * CKQ) {  // left through the top edge at tile column code - 1 (0: through the corner)
+        i = row0;
+        j = col0 + code;
+      } else {  // left through the left edge at tile row code - 129
+        i = row0 + code - 4 * CKQ;
+        j = col0;
+      }
+    } else {
+      // outside the band (or entered in the interior: a pair's first tile).  Unless this is the chapter's
+      // first tile or the last chapter, end the chapter here: the next one is centred on this tile.
+      if (!last && ntiles > 0) break;
+      const int tq = (lj >> 2) + 1, tmax = li / RT;
+      recompute_tile<MODE, ADDMODE, true, RT>(T, hs, cb, tq, tmax, tq + tmax, smem, lane);
+      __syncwarp();
+      walk_tile<RT>(smem, row0, col0, i, j, W, a.pxy, a.pgap, lane);
+      __syncwarp();
+      ++misses;
+    }
+    ++ntiles;
+  }
+  S->cost[lane] = W.cost;
+  if (lane == 0) {
+    S->i = i;
+    S->j = j;
+    S->pos = W.pos;
+    S->done = (i > 0 && j > 0) ? 0 : 1;
+    S->misses = misses;
+    S->nvisits = nlist;
+    if (chapter == 0) S->cost_emit = 0;
+    // slope for the next chapter: this chapter's displacement, up to the tile the next one starts in
+    // (after a turn that is the tile which ended this chapter: the new direction shows at once)
+    const int dhs = g.hs0 - (max(i, 1) - 1) / TILE_ROWS, dcb = g.cb0 - (max(j, 1) - 1) / (4 * CKQ);
+    if (dhs + dcb > 0 || chapter == 0) {
+      S->dhs = dhs;
+      S->dcb = dcb;
+    }
+  }
+}
+
+template <int MODE, int ADDMODE>
+__global__ void __launch_bounds__(32 * BAND_WARPS) traceback_band_emit_kernel(const TracebackArgs a) {
+  constexpr int RT = RT_WARP;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t p = blockIdx.y;
+  BandState *S = a.band_state + p;
+  const int e = (int)blockIdx.x * BAND_WARPS + warp;
+  if (e >= S->nvisits) return;
+  const BandVisit V = a.band_visits[(uint64_t)p * (uint64_t)a.band_visit_cap + (uint64_t)e];
+  const PairDesc P = a.pairs[p];
+  const TileCtx T = make_ctx<MODE>(a, P);
+  uint8_t *tile = smem + (size_t)warp * LONG_TILE_BYTES;
+  const uint4 *src = reinterpret_cast<const uint4 *>(band_image(a, p, V.slot));
+  uint4 *dst = reinterpret_cast<uint4 *>(tile);
+#pragma unroll
+  for (int r = 0; r < TILE_DIR_BYTES / 16 / 32; ++r) dst[lane + 32 * r] = __ldcg(src + lane + 32 * r);
+  const int row0 = V.hs * TILE_ROWS, col0 = V.cb * 4 * CKQ;
+  stage_tile_chars<RT, TILE_ROWS / RT>(T, row0, col0, tile, lane);
+  __syncwarp();
+  PathOut W{a.out + P.out_off, a.out + P.out_off + P.cap, V.pos, 0};
+  int i = row0 + (V.cell & 0xffff) + 1, j = col0 + (V.cell >> 16) + 1;
+  walk_tile<RT>(tile, row0, col0, i, j, W, a.pxy, a.pgap, lane);
+  int cost = W.cost;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, d);
+  if (lane == 0 && cost) atomicAdd(&S->cost_emit, cost);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32) traceback_band_finish_kernel(const TracebackArgs a) {
+  const int lane = threadIdx.x;
+  const uint32_t p = blockIdx.x;
+  const BandState *S = a.band_state + p;
+  const PairDesc P = a.pairs[p];
+  const TileCtx T = make_ctx<MODE>(a, P);
+  PathOut W{a.out + P.out_off, a.out + P.out_off + P.cap, S->pos, S->cost[lane] + (lane == 0 ? S->cost_emit : 0)};
+  finish_pair<32>(a, T, p, S->i, S->j, W, lane, 0xffffffffu, 0);
+}
+
+template <int MODE, int ADDMODE>
+static cudaError_t launch_band(const TracebackArgs &args, cudaStream_t stream) {
+  const int images = (args.band_levels + 1) * (2 * args.band_halfwidth + 1);
+  const dim3 pgrid((unsigned)((images + BAND_WARPS - 1) / BAND_WARPS), args.npairs);
+  const dim3 egrid((unsigned)((args.band_visit_cap + BAND_WARPS - 1) / BAND_WARPS), args.npairs);
+  for (int c = 0; c < args.band_chapters; ++c) {
+    traceback_band_produce_kernel<MODE, ADDMODE>
+        <<<pgrid, 32 * BAND_WARPS, BAND_WARPS * LONG_TILE_BYTES, stream>>>(args, c);
+    traceback_band_hop_kernel<MODE, ADDMODE><<<args.npairs, 32, LONG_TILE_BYTES, stream>>>(args, c, c + 1 == args.band_chapters);
+    traceback_band_emit_kernel<MODE, ADDMODE><<<egrid, 32 * BAND_WARPS, BAND_WARPS * LONG_TILE_BYTES, stream>>>(args);
+  }
+  traceback_band_finish_kernel<MODE><<<args.npairs, 32, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
 template <int MODE, int ADDMODE>
 static cudaError_t launch_tiles(const TracebackArgs &args, cudaStream_t stream) {
+  if (args.band) return launch_band<MODE, ADDMODE>(args, stream);
   if (args.long_pairs) {
     const size_t smem = (size_t)LONG_SLOTS * LONG_TILE_BYTES;
     cudaError_t e = cudaFuncSetAttribute(traceback_tiles_long_kernel<MODE, ADDMODE>,

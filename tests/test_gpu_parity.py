@@ -316,6 +316,25 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     {"SEQALK_FILL16": "0", "SEQALK_TB_LONG": "0"},
     {"SEQALK_FILL16": "0", "SEQALK_TB_LONG": "0", "SEQALK_TB_HALF": "0"},
     {"SEQALK_FILL16": "0", "SEQALK_TB_LONG": "0", "SEQALK_FORCE_GENERAL": "1"},
+    # banded traceback in chapters (the path of a few LONG pairs), forced onto this small job: default
+    # chapter length, chapters of 4 levels with a band of 3 tiles, chapters of ONE level without
+    # neighbours (most tiles are recomputed by the walking warp), every fill under it, several batches;
+    # per-pair hashes computed by the host
+    {"SEQALK_TB_BAND": "1"},
+    {"SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_LEVELS": "3", "SEQALK_TB_BAND_HALFWIDTH": "1"},
+    {"SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_LEVELS": "0", "SEQALK_TB_BAND_HALFWIDTH": "0"},
+    {"SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_LEVELS": "5", "SEQALK_FILL16": "0"},
+    {"SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_LEVELS": "2", "SEQALK_FORCE_GENERAL": "1"},
+    {"SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_LEVELS": "7", "SEQALK_FILL_TAB": "0", "SEQALK_DIR_BUDGET_GB": "0.001"},
+    {"SEQALK_HOST_HASH": "1"},
+    # thin strip pairs of the packed fill (512 / 256 rows: the few-long-pairs geometry) under every traceback
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "4"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_TB_LONG": "0"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "4", "SEQALK_TB_LONG": "0", "SEQALK_DIR_BUDGET_GB": "0.001"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "4", "SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_LEVELS": "3"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_CHAPTERS": "2"},
+    {"SEQALK_HOST_HASH": "1", "SEQALK_TB_BAND": "1", "SEQALK_DIR_BUDGET_GB": "0.001"},
 ], ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
 def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatch, env):
     """Rows per lane (8/16), cost by compare or by 4-letter table, adds on ALU or FMA pipe,
@@ -410,6 +429,33 @@ def test_traceback_modes_on_long_and_skewed_pairs(seqalk, oracle, workloads, mon
     assert np.array_equal(pen, op)
     assert [d.tobytes().hex() for d in dig] == oh
     # one long pair through getMinimumPenalty (arrays) in this mode
+    x, y = genes[0], genes[2]
+    pen1, xans, yans = seqalk.get_minimum_penalty(x, y, 3, 2)
+    open_, a1, a2, _ = oracle.pair(x, y, 3, 2)
+    assert pen1 == open_ and seqalk.alignment_strings(xans, yans) == (a1, a2)
+
+
+@pytest.mark.parametrize("levels,halfwidth", [(63, 4), (8, 1), (1, 0), (200, 2)])
+def test_banded_traceback_on_long_and_skewed_pairs(seqalk, oracle, monkeypatch, levels, halfwidth):
+    """The banded traceback (produce the tiles near the straight line to the origin, then walk) on pairs
+    whose path does NOT follow that line — very unequal lengths, a substring pair (the path runs along
+    the diagonal and ends in one long gap) — so that part of the tiles come from the band and part are
+    recomputed by the walking warp; chapter lengths from 2 levels to the whole pair."""
+    monkeypatch.setenv("SEQALK_TB_BAND", "1")
+    monkeypatch.setenv("SEQALK_TB_BAND_LEVELS", str(levels))
+    monkeypatch.setenv("SEQALK_TB_BAND_HALFWIDTH", str(halfwidth))
+    rnd = random.Random(29)
+    base = bytes(rnd.choice(b"ACGT") for _ in range(9000))
+    genes = [base, base[1200:7700], bytes(rnd.choice(b"ACGT") for _ in range(7000)),
+             bytes(rnd.choice(b"ACGT") for _ in range(300)), bytes(rnd.choice(b"ACGT") for _ in range(2049)),
+             base[::-1][:3000], b"A" * 1500]
+    with seqalk.Job(genes, 3, 2) as job:
+        job.run()
+        pen, dig = job.fetch()
+        assert job.stats().tile_mode == 1
+    od, op, oh = oracle.all_pairs(genes, 3, 2, want_pair_hashes=True)
+    assert np.array_equal(pen, op)
+    assert [d.tobytes().hex() for d in dig] == oh
     x, y = genes[0], genes[2]
     pen1, xans, yans = seqalk.get_minimum_penalty(x, y, 3, 2)
     open_, a1, a2, _ = oracle.pair(x, y, 3, 2)
