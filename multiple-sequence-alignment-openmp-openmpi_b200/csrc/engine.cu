@@ -466,10 +466,38 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   // few-pair jobs take 1024-row ones: more strip pairs in flight (big13 fill 46 -> 41 ms against the
   // 32-bit fill, the lone 200k x 200k pair 26 -> 24 ms; with 2048-row pairs 31 ms)
   main_rp_ = few_pairs_ ? 16 : 32;
+  // Kernel build and residency (same-box A/B, profiles/r02b_*):
+  //  * many pairs: predicated checkpoint stores, 3 CTAs per SM (134 registers): cfg4 job 4.69 -> 4.61 s;
+  //  * few long pairs, more strip pairs than the GPU has warp schedulers (big13): 1024-row strip pairs,
+  //    predicated checkpoint stores, only 2 CTAs per SM — the queue is ordered critical path first,
+  //    and fewer resident warps means the earliest (most critical) strip pairs run at full speed:
+  //    fill 40.5 ms (6 CTAs per SM, branch) -> 35.5 (4, predicated) -> 30.5 (2);
+  //  * a handful of long pairs whose 512-row strip pairs all find a scheduler of their own (the lone
+  //    200k x 200k pair): 512-row strip pairs, predicated stores, pipelined hand-off: fill 24.5 -> 16.8 ms.
+  fill16_flags_ = FILL16_PREDCK;
+  fill16_minb_ = few_pairs_ ? 3 : 3;
+  fill16_cap_ = few_pairs_ ? 2 : 0;
+  if (few_pairs_) {
+    uint64_t thin = 0;  // 512-row strip pairs of the job
+    for (const TaskIJ &tk : tasks_) thin += (uint64_t)(std::max(pack_->len[tk.i], 1) + 511) / 512;
+    if (thin <= 6ull * (uint64_t)sm_count_) {
+      main_rp_ = 8;
+      fill16_flags_ = FILL16_PREDCK | FILL16_PIPE;
+      fill16_minb_ = 4;
+      fill16_cap_ = 0;
+    }
+  }
   if (const char *e = std::getenv("SEQALK_FILL16_RP")) {
     const int v = std::atoi(e);
     main_rp_ = (v == 16 || v == 8 || v == 4) ? v : 32;  // 8 / 4: strip pairs of 512 / 256 rows (one-launch kernel only)
+    if (main_rp_ != 8) fill16_flags_ &= ~FILL16_PIPE;
   }
+  if (const char *e = std::getenv("SEQALK_FILL16_PREDCK")) fill16_flags_ = (fill16_flags_ & ~FILL16_PREDCK) | (std::atoi(e) ? FILL16_PREDCK : 0);
+  if (const char *e = std::getenv("SEQALK_FILL16_PIPE")) fill16_flags_ = (fill16_flags_ & ~FILL16_PIPE) | (std::atoi(e) ? FILL16_PIPE : 0);
+  if (main_rp_ == 4) fill16_flags_ = 0;
+  if (!(fill16_flags_ & FILL16_PREDCK)) fill16_minb_ = 0;  // the branch builds: their own defaults (4 / 6 / 8 CTAs per SM)
+  if (variant_.minb > 0) fill16_minb_ = variant_.minb;     // SEQALK_FILL_MINB
+  if (const char *e = std::getenv("SEQALK_FILL_CTAS_PER_SM")) fill16_cap_ = std::max(0, std::atoi(e));
   if (tiles_ && variant_.mode == MODE_TAB && variant_.R == 32 && mixed_ && codes_.p) {
     fill16_shift_ = fill16_rebase_shift(pxy, pgap, main_rp_);
     if (!fill16_shift_ && main_rp_ == 32) {
@@ -836,7 +864,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.main_rp = main_rp_;
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 0], st));
     if (one_launch) {
-      SEQALK_CUDA(launch_fill16(fa, 100 + main_rp_, variant_.minb, sm_count_, st));
+      SEQALK_CUDA(launch_fill16(fa, 100 + main_rp_, fill16_minb_, sm_count_, st, fill16_flags_, fill16_cap_));
     } else if (fill16_shift_) {
       SEQALK_CUDA(launch_fill16(fa, main_rp_, variant_.minb, sm_count_, st));
     } else {
@@ -927,8 +955,12 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       if (const char *e = std::getenv("SEQALK_TB_BAND")) band = std::atoi(e) != 0 && B.count <= 4096;
       if (band) {
         ta.band = 1;
-        ta.band_levels = 63;
-        ta.band_halfwidth = B.count <= 8 ? 4 : 2;
+        // a handful of pairs: long chapters, wide band (the produce launch is far from filling the GPU);
+        // more pairs: the produce launches are the cost — short chapters, three tiles per level
+        // (same box, traceback of the 200k x 200k pair: 3.6 ms at 63 / 4, 2.8 ms at 127 / 4; of the 78 pairs
+        // of big13: 8.5 ms at 63 / 2, 6.8 ms at 31 / 1)
+        ta.band_levels = B.count <= 8 ? 127 : 31;
+        ta.band_halfwidth = B.count <= 8 ? 4 : 1;
         if (const char *e = std::getenv("SEQALK_TB_BAND_LEVELS")) ta.band_levels = std::max(0, std::min(1023, std::atoi(e)));
         if (const char *e = std::getenv("SEQALK_TB_BAND_HALFWIDTH")) ta.band_halfwidth = std::max(0, std::min(16, std::atoi(e)));
         // chapters: what a path that stays inside its bands needs, plus a quarter for chapters cut
@@ -983,7 +1015,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       da.small_regs = 1;
       if (const char *e = std::getenv("SEQALK_DIGEST_CAP")) da.small_regs = std::atoi(e) ? 1 : 0;
       // A few very long strings: SHA-512 is serial per string, and one GPU lane hashes ~27 MB/s
-      // against ~260 MB/s of a host core (the 200k x 200k pair: 15 ms on the GPU).  Such a batch's
+      // (less when the lanes of a warp hash strings of different lengths) against ~260 MB/s of a host core.  Such a batch's
       // strings are brought to the host, hashed there by a few threads and the 64-byte digests
       // uploaded; the kernel then only publishes the penalties and runs the self-check.
       // SEQALK_HOST_HASH=0 / 1 forces it off / on.
@@ -997,8 +1029,9 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
         }
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const double threads = (double)std::min<uint64_t>(std::min<uint64_t>(hw, 16), 2 * B.count);
-        const double device_ns = 37.5 * (double)longest, host_ns = 4.0 * (double)total / threads + 100e3;
-        bool host = few_pairs_ && B.count > 0 && 2.0 * host_ns < device_ns;
+        // measured: the 200k x 200k pair 15.3 ms -> 0.6 ms, the 78 pairs of big13 (18.7 MB of strings) 10.2 -> 3.2 ms
+        const double device_ns = 55.0 * (double)longest, host_ns = 4.0 * (double)total / threads + 100e3;
+        bool host = few_pairs_ && B.count > 0 && host_ns < device_ns;
         if (const char *e = std::getenv("SEQALK_HOST_HASH")) host = std::atoi(e) != 0 && B.count > 0;
         if (host) {
           host_hash_batch(S, G, B.count, B.out_bytes, digests_dev, hs, st);

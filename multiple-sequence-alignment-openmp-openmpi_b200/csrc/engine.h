@@ -165,6 +165,7 @@ class DeviceWorker {
   FillVariant variant_;
   bool few_pairs_ = false;  // fewer strips than ~2x the resident warps: wavefront-bound job
   bool mixed_ = false;  // tile mode, R = 32: half-height last strips (second fill launch)
+  int fill16_flags_ = 0, fill16_minb_ = 0, fill16_cap_ = 0;  // one-launch packed fill: build (FILL16_*), register budget, resident CTAs per SM
   int main_rp_ = 16;      // packed fill: rows per half lane of the main strip pairs (32: 2048-row strip pairs + 1024 / 512-row tails)
   StripGeom geometry(int m) const {
     if (fill16_shift_ && main_rp_ <= 8) return strip_geometry(m, 2 * main_rp_, false);  // uniform strip pairs of 64 * main_rp_ rows

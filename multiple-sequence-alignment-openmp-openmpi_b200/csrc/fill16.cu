@@ -42,6 +42,7 @@
 //     checkpoint column at the same step, image e = [rows of A at checkpoint e | rows of B at
 //     checkpoint e - 1].  The traceback unpacks with the logged base.
 #include <algorithm>
+#include <cstdlib>
 
 #include "fill_core.cuh"
 
@@ -110,12 +111,46 @@ __device__ __forceinline__ void macro_step16(unsigned (&h)[RP], unsigned &dg, co
   }
 }
 
+// macro_step16 that also hands the block's bottom row to the next lane as soon as a column is done
+// (PIPE, jobs of a few long pairs: a warp alone on its scheduler would otherwise wait out the shuffle
+// latency at the top of every step; only the last column's shuffle is still on the critical path).
+template <int RP>
+__device__ __forceinline__ void macro_step16_sh(unsigned (&h)[RP], unsigned &dg, const unsigned (&tl)[RP],
+                                                const unsigned (&th)[RP], const unsigned (&up_in)[4], unsigned sel01,
+                                                unsigned sel23, unsigned one, unsigned (&outv)[4], unsigned (&sh)[4],
+                                                int src_lane) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const unsigned w = c < 2 ? sel01 : sel23;
+    const unsigned sel = (c & 1) ? (w >> 16) : w;
+    unsigned diag = dg, up = up_in[c];
+    dg = up;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+      const unsigned left = h[r];
+      const unsigned cost = prmt(tl[r], th[r], sel);
+      unsigned t;
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(diag), "r"(one), "r"(cost));
+      const unsigned v = __vimax3_u16x2(left, up, t);
+      diag = left;
+      up = v;
+      h[r] = v;
+    }
+    outv[c] = up;
+    sh[c] = __shfl_sync(0xffffffffu, up, src_lane);
+  }
+}
+
 // Cost table of one DP row in the max domain: byte q = gain of the row's letter against letter q.
 __device__ __forceinline__ unsigned row_table16(bool inside, unsigned ch, unsigned cm, unsigned cx) {
   return inside ? ((cx * 0x01010101u) ^ ((cm ^ cx) << (ch & 24u))) : 0u;  // ch = 8 * letter code
 }
 
-template <int RP>
+// PREDCK: the column checkpoints are written by predicated stores through a per-lane running pointer
+// instead of a branch that one lane takes at every step (see below).
+// PIPE: the lane hand-off is shuffled as soon as a column is done (macro_step16_sh) and the staged
+// entries of the next step are read from shared memory one step ahead.
+template <int RP, bool PREDCK = false, bool PIPE = false>
 __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const PairDesc &P, const int s,
                                                    const int row_base, const int lane, uint2 *ring_sel,
                                                    int4 *ring_top) {
@@ -187,6 +222,7 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
 #pragma unroll
   for (int r = 0; r < RP; ++r) h[r] = 0u;
   unsigned dg = 0u, outv[4] = {0u, 0u, 0u, 0u};
+  unsigned sh[4] = {0u, 0u, 0u, 0u};  // PIPE: outv of the lane above (lane 31's for lane 0), already shuffled
   int negbase = 0;  // -(base): absolute G = relative - negbase, H' = negbase - relative
   const unsigned merge = lane == 0 ? 0x1054u : 0x3210u;  // lane 0: low half <- top row, high half <- lane 31's low half
   const int src_lane = (lane + 31) & 31;
@@ -198,6 +234,12 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
   const uint8_t *sel_rd = reinterpret_cast<const uint8_t *>(ring_sel + 64 - lane);
   const uint8_t *top_rd = reinterpret_cast<const uint8_t *>(ring_top);
   int qcA = -lane;  // macro column of the low halves at step q
+  // PREDCK: this lane stores image k - 1 when its low halves have finished macro column 32 * k - 1,
+  // k = 1 .. ck_last (the same set of stores as the branch below makes): next such column + 1, and
+  // where the image goes
+  const int ck_last = ((nq - 1) >> 5) >= 1 ? ((nq - 1) >> 5) + 1 : 0;
+  int ck_next = ck_last >= 1 ? 32 : 0x7fffffff;
+  uint32_t *ckp = ck;
 
   __syncwarp();
   ring_sel[32 + lane] = ring_sel[96 + lane] = make_uint2(SEL_NULL, SEL_NULL);  // entries -31..-1: halves not started yet
@@ -217,6 +259,8 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
       for (int r = 0; r < RP; ++r) h[r] -= dd;  // both halves >= delta: no borrow across
 #pragma unroll
       for (int c = 0; c < 4; ++c) outv[c] -= dd;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sh[c] -= dd;
       dg -= dd;
       negbase -= (int)delta;
       if (lane == 0) blog[q0 >> KS] = -negbase;
@@ -259,19 +303,38 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
     __syncwarp();
 
     const int send = min(32, nsteps - q0);
+    int4 tv4_next = make_int4(0, 0, 0, 0);
+    uint2 sw_next = make_uint2(0u, 0u);
+    if constexpr (PIPE) {  // the first step's staged entries
+      tv4_next = *reinterpret_cast<const int4 *>(top_rd);
+      sw_next = *reinterpret_cast<const uint2 *>(sel_rd + 8 * (q0 & 63));
+    }
 #pragma unroll 1  // keeps the rows in fixed registers (vector stores of the checkpoints without moves)
     for (int st = 0; st < send; ++st) {
       // ---- neighbours: every lane takes the bottom rows of the lane above (both halves); lane 0
       // takes lane 31's low half (bottom row of strip A) as its high half and the staged top row as
       // its low half
-      const int4 tv4 = *reinterpret_cast<const int4 *>(top_rd + 16 * st);
-      unsigned up_in[4];
-      up_in[0] = prmt(__shfl_sync(FULL, outv[0], src_lane), (unsigned)tv4.x, merge);
-      up_in[1] = prmt(__shfl_sync(FULL, outv[1], src_lane), (unsigned)tv4.y, merge);
-      up_in[2] = prmt(__shfl_sync(FULL, outv[2], src_lane), (unsigned)tv4.z, merge);
-      up_in[3] = prmt(__shfl_sync(FULL, outv[3], src_lane), (unsigned)tv4.w, merge);
-      const uint2 sw = *reinterpret_cast<const uint2 *>(sel_rd + 8 * ((q0 + st) & 63));
-      macro_step16<RP>(h, dg, tl, th, up_in, sw.x, sw.y, one, outv);
+      if constexpr (PIPE) {
+        const int4 tv4 = tv4_next;
+        const uint2 sw = sw_next;
+        tv4_next = *reinterpret_cast<const int4 *>(top_rd + 16 * ((st + 1) & 31));  // (slot 0 after the block's last step: unused)
+        sw_next = *reinterpret_cast<const uint2 *>(sel_rd + 8 * ((q0 + st + 1) & 63));
+        unsigned up_in[4];
+        up_in[0] = prmt(sh[0], (unsigned)tv4.x, merge);
+        up_in[1] = prmt(sh[1], (unsigned)tv4.y, merge);
+        up_in[2] = prmt(sh[2], (unsigned)tv4.z, merge);
+        up_in[3] = prmt(sh[3], (unsigned)tv4.w, merge);
+        macro_step16_sh<RP>(h, dg, tl, th, up_in, sw.x, sw.y, one, outv, sh, src_lane);
+      } else {
+        const int4 tv4 = *reinterpret_cast<const int4 *>(top_rd + 16 * st);
+        unsigned up_in[4];
+        up_in[0] = prmt(__shfl_sync(FULL, outv[0], src_lane), (unsigned)tv4.x, merge);
+        up_in[1] = prmt(__shfl_sync(FULL, outv[1], src_lane), (unsigned)tv4.y, merge);
+        up_in[2] = prmt(__shfl_sync(FULL, outv[2], src_lane), (unsigned)tv4.z, merge);
+        up_in[3] = prmt(__shfl_sync(FULL, outv[3], src_lane), (unsigned)tv4.w, merge);
+        const uint2 sw = *reinterpret_cast<const uint2 *>(sel_rd + 8 * ((q0 + st) & 63));
+        macro_step16<RP>(h, dg, tl, th, up_in, sw.x, sw.y, one, outv);
+      }
 
       // ---- kept rows (absolute H'): tile traceback, hand-off to the next strip pair, corner.
       // Predicated stores, no branch: the conversions run on the FMA pipe, which has room.
@@ -291,7 +354,20 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
       // ---- column checkpoints: the packed registers as they are.  One lane at a time takes this
       // branch (every lane once per 32 steps), so it is kept short: consecutive stores of a lane go
       // to consecutive images (k, low halves), (k, high halves), (k+1, low halves), ...
-      if (((qcA + 1) & 31) == 0) {
+      if constexpr (PREDCK) {
+        static_assert(!PREDCK || (CKQ == 32 && RP >= 8), "predicated checkpoint stores: a checkpoint every 32 macro columns");
+        const int hit = (qcA + 1 == ck_next) ? 1 : 0;
+#pragma unroll
+        for (int r8 = 0; r8 < RP / 8; ++r8)
+          asm volatile("{.reg .pred p; setp.ne.s32 p, %9, 0; @p st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};}" ::"l"(ckp + 8 * r8),
+                       "r"(h[8 * r8]), "r"(h[8 * r8 + 1]), "r"(h[8 * r8 + 2]), "r"(h[8 * r8 + 3]), "r"(h[8 * r8 + 4]),
+                       "r"(h[8 * r8 + 5]), "r"(h[8 * r8 + 6]), "r"(h[8 * r8 + 7]), "r"(hit)
+                       : "memory");
+        if (hit) {
+          ckp += halfwords;
+          ck_next = ck_next + 32 <= 32 * ck_last ? ck_next + 32 : 0x7fffffff;
+        }
+      } else if (((qcA + 1) & 31) == 0) {
         const int ckcol = (qcA + 1) >> 5;
         bool store;
         uint32_t *dst;
@@ -362,7 +438,7 @@ __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_kernel(const FillArg
 // predecessor through the same progress counters as every other strip pair.  One queue, one
 // ramp-down per batch instead of three (the tail launches of a small batch — one GPU's share of a
 // chunk on 8 GPUs — are shorter than one wave of warps).
-template <int MAINRP, int MINB>
+template <int MAINRP, int MINB, bool PREDCK = false, bool PIPE = false>
 __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_all_kernel(const FillArgs a) {
   __shared__ uint2 s_sel[F16_THREADS / 32][128];
   __shared__ int4 s_top[F16_THREADS / 32][32];
@@ -377,11 +453,11 @@ __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_all_kernel(const Fil
     const int s = (int)task.strip;
     const int nmain = main_strips(P.nstrips, P.half_last);
     if (s < nmain)
-      process_strip_pair<MAINRP>(a, P, s, s * (64 * MAINRP), lane, s_sel[warp], s_top[warp]);
+      process_strip_pair<MAINRP, PREDCK && MAINRP >= 8, PIPE>(a, P, s, s * (64 * MAINRP), lane, s_sel[warp], s_top[warp]);
     else if (MAINRP == 32 && (P.half_last & 2) && s == nmain)
-      process_strip_pair<16>(a, P, s, nmain * 2048, lane, s_sel[warp], s_top[warp]);
+      process_strip_pair<16, PREDCK>(a, P, s, nmain * 2048, lane, s_sel[warp], s_top[warp]);
     else
-      process_strip_pair<8>(a, P, s, (int)P.mpad - 512, lane, s_sel[warp], s_top[warp]);
+      process_strip_pair<8, PREDCK>(a, P, s, (int)P.mpad - 512, lane, s_sel[warp], s_top[warp]);
   }
 }
 
@@ -409,16 +485,29 @@ __global__ void build_sel16_kernel(const uint8_t *__restrict__ codes, uint8_t *_
 }
 
 typedef void (*Fill16Ptr)(const FillArgs);
-Fill16Ptr pick16_all(int rp, int minb) {
-  if (rp == 32) return minb == 3 ? fill16_all_kernel<32, 3> : fill16_all_kernel<32, 4>;
-  if (rp == 16) return minb == 5 ? fill16_all_kernel<16, 5> : fill16_all_kernel<16, 6>;
+// the one-launch kernel; flags: FILL16_PREDCK / FILL16_PIPE
+Fill16Ptr pick16_all(int rp, int minb, int flags) {
+  const bool predck = flags & FILL16_PREDCK, pipe = flags & FILL16_PIPE;
+  if (rp == 32) {
+    // 128 registers without spills = 4 CTAs per SM; with the predicated checkpoint stores the 3-CTA build
+    // (134 registers) is the faster one (cfg4 job 4.69 s -> 4.61 s, same box)
+    if (predck) return minb == 4 ? fill16_all_kernel<32, 4, true> : fill16_all_kernel<32, 3, true>;
+    return minb == 3 ? fill16_all_kernel<32, 3> : fill16_all_kernel<32, 4>;
+  }
+  if (rp == 16) {
+    if (predck) return minb == 6 ? fill16_all_kernel<16, 6, true> : fill16_all_kernel<16, 3, true>;
+    return minb == 5 ? fill16_all_kernel<16, 5> : fill16_all_kernel<16, 6>;
+  }
   // thin strip pairs (512 / 256 rows) for jobs of a few long pairs: more warps along the wavefront
-  if (rp == 8) return fill16_all_kernel<8, 8>;
+  if (rp == 8) {
+    if (predck && pipe) return minb == 8 ? fill16_all_kernel<8, 8, true, true> : fill16_all_kernel<8, 4, true, true>;
+    return predck ? fill16_all_kernel<8, 8, true> : fill16_all_kernel<8, 8>;
+  }
   if (rp == 4) return fill16_all_kernel<4, 8>;
   return nullptr;
 }
-Fill16Ptr pick16(int rp, int minb) {
-  if (rp >= 100) return pick16_all(rp - 100, minb);  // 100 + main rp: the one-launch kernel
+Fill16Ptr pick16(int rp, int minb, int flags) {
+  if (rp >= 100) return pick16_all(rp - 100, minb, flags);  // 100 + main rp: the one-launch kernel
   // 32 rows per half lane: 128 registers without spills = 4 CTAs per SM (cfg4 fill 4.14 s; 3 CTAs: 4.20 s)
   if (rp == 32) return minb == 3 ? fill16_kernel<32, 3> : fill16_kernel<32, 4>;
   if (rp == 16) {
@@ -455,20 +544,22 @@ cudaError_t launch_build_sel16(const uint8_t *codes, uint8_t *sel16, const uint3
   return cudaGetLastError();
 }
 
-int fill16_blocks_per_sm(int rp, int minb) {
-  Fill16Ptr k = pick16(rp, minb);
+int fill16_blocks_per_sm(int rp, int minb, int flags) {
+  Fill16Ptr k = pick16(rp, minb, flags);
   if (!k) return 0;
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, F16_THREADS, 0);
   return nb;
 }
 
-cudaError_t launch_fill16(const FillArgs &args, int rp, int minb, int sm_count, cudaStream_t stream) {
+cudaError_t launch_fill16(const FillArgs &args, int rp, int minb, int sm_count, cudaStream_t stream, int flags,
+                          int max_ctas_per_sm) {
   if (args.ntasks == 0) return cudaSuccess;
-  Fill16Ptr k = pick16(rp, minb);
+  Fill16Ptr k = pick16(rp, minb, flags);
   if (!k) return cudaErrorInvalidValue;
-  const int nb = fill16_blocks_per_sm(rp, minb);
+  int nb = fill16_blocks_per_sm(rp, minb, flags);
   if (nb < 1) return cudaErrorLaunchOutOfResources;
+  if (max_ctas_per_sm > 0) nb = std::min(nb, max_ctas_per_sm);  // fewer resident strip pairs, each of them faster
   long long want = ((long long)args.ntasks + (F16_THREADS / 32) - 1) / (F16_THREADS / 32);
   long long grid = (long long)sm_count * nb;
   if (grid > want) grid = want;

@@ -651,7 +651,8 @@ __global__ void __launch_bounds__(128) traceback_tiles_long_kernel(const Traceba
 // on the band.  A FINISH launch writes the tails and the result records.
 struct BandGeom {
   int hs0, cb0, L0, W1;
-  long long num, den;  // slope of the centre line: tile rows per level = num / den
+  float slope;  // of the centre line: tile rows per level (the produce and the hop launches evaluate the same
+                // expression on the same inputs, so they agree on every tile's slot)
 };
 __device__ __forceinline__ BandGeom band_geom(const TracebackArgs &a, int i0, int j0, int dhs, int dcb) {
   BandGeom g;
@@ -659,18 +660,15 @@ __device__ __forceinline__ BandGeom band_geom(const TracebackArgs &a, int i0, in
   g.cb0 = (j0 - 1) / (4 * CKQ);
   g.L0 = g.hs0 + g.cb0;
   g.W1 = 2 * a.band_halfwidth + 1;
-  if (dhs + dcb > 0) {  // the previous chapter's displacement
-    g.num = dhs;
-    g.den = dhs + dcb;
-  } else {  // towards DP cell (0, 0)
-    g.num = i0;
-    g.den = (long long)i0 + j0;
-  }
+  if (dhs + dcb > 0)  // the previous chapter's displacement
+    g.slope = __fdividef((float)dhs, (float)(dhs + dcb));
+  else  // towards DP cell (0, 0)
+    g.slope = __fdividef((float)i0, (float)i0 + (float)j0);
   return g;
 }
 // tile row of the band's centre, d levels below the chapter's first tile
 __device__ __forceinline__ int band_center(const BandGeom &g, int d) {
-  return g.hs0 - (int)(((long long)d * g.num + (g.den >> 1)) / g.den);
+  return g.hs0 - (int)__fmaf_rn((float)d, g.slope, 0.5f);
 }
 // index of tile (hs, cb) among the chapter's images, -1: not part of the band
 __device__ __forceinline__ int band_slot(const TracebackArgs &a, const BandGeom &g, int hs, int cb) {

@@ -334,7 +334,17 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "4", "SEQALK_TB_LONG": "0", "SEQALK_DIR_BUDGET_GB": "0.001"},
     {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "4", "SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_LEVELS": "3"},
     {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_TB_BAND": "1", "SEQALK_TB_BAND_CHAPTERS": "2"},
-    {"SEQALK_HOST_HASH": "1", "SEQALK_TB_BAND": "1", "SEQALK_DIR_BUDGET_GB": "0.001"},
+    # packed fill builds: column checkpoints by the one-lane branch instead of predicated stores through a
+    # running pointer (the default), register budgets, pipelined lane hand-off, resident CTAs per SM
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_PREDCK": "0", "SEQALK_TB_LONG": "0"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_PREDCK": "0", "SEQALK_FILL_MINB": "3", "SEQALK_TB_LONG": "0"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL_MINB": "4", "SEQALK_TB_LONG": "0", "SEQALK_DIR_BUDGET_GB": "0.001"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "16", "SEQALK_FILL_MINB": "6"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "16", "SEQALK_FILL16_PREDCK": "0", "SEQALK_FILL_CTAS_PER_SM": "1"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_FILL16_PIPE": "0"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_FILL16_PIPE": "1", "SEQALK_FILL_MINB": "8"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_FILL16_PREDCK": "0", "SEQALK_FILL16_PIPE": "0",
+     "SEQALK_DIR_BUDGET_GB": "0.001"},
 ], ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
 def test_every_kernel_variant_is_bit_exact(seqalk, oracle, workloads, monkeypatch, env):
     """Rows per lane (8/16), cost by compare or by 4-letter table, adds on ALU or FMA pipe,
