@@ -474,15 +474,15 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   //    fill 40.5 ms (6 CTAs per SM, branch) -> 35.5 (4, predicated) -> 30.5 (2);
   //  * a handful of long pairs whose 512-row strip pairs all find a scheduler of their own (the lone
   //    200k x 200k pair): 512-row strip pairs, predicated stores, pipelined hand-off: fill 24.5 -> 16.8 ms.
-  fill16_flags_ = FILL16_PREDCK;
-  fill16_minb_ = few_pairs_ ? 3 : 3;
+  fill16_flags_ = few_pairs_ ? (FILL16_PREDCK | FILL16_SENT) : FILL16_PREDCK;
+  fill16_minb_ = 3;
   fill16_cap_ = few_pairs_ ? 2 : 0;
   if (few_pairs_) {
     uint64_t thin = 0;  // 512-row strip pairs of the job
     for (const TaskIJ &tk : tasks_) thin += (uint64_t)(std::max(pack_->len[tk.i], 1) + 511) / 512;
     if (thin <= 6ull * (uint64_t)sm_count_) {
       main_rp_ = 8;
-      fill16_flags_ = FILL16_PREDCK | FILL16_PIPE;
+      fill16_flags_ = FILL16_PREDCK | FILL16_PIPE | FILL16_SENT;
       fill16_minb_ = 4;
       fill16_cap_ = 0;
     }
@@ -494,7 +494,10 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
   }
   if (const char *e = std::getenv("SEQALK_FILL16_PREDCK")) fill16_flags_ = (fill16_flags_ & ~FILL16_PREDCK) | (std::atoi(e) ? FILL16_PREDCK : 0);
   if (const char *e = std::getenv("SEQALK_FILL16_PIPE")) fill16_flags_ = (fill16_flags_ & ~FILL16_PIPE) | (std::atoi(e) ? FILL16_PIPE : 0);
+  if (const char *e = std::getenv("SEQALK_FILL16_SENT")) fill16_flags_ = (fill16_flags_ & ~FILL16_SENT) | (std::atoi(e) ? FILL16_SENT : 0);
   if (main_rp_ == 4) fill16_flags_ = 0;
+  if ((main_rp_ != 8 && main_rp_ != 16) || !(fill16_flags_ & FILL16_PREDCK)) fill16_flags_ &= ~FILL16_SENT;
+  if (main_rp_ == 8 && !(fill16_flags_ & FILL16_PIPE)) fill16_flags_ &= ~FILL16_SENT;  // (no such build)
   if (!(fill16_flags_ & FILL16_PREDCK)) fill16_minb_ = 0;  // the branch builds: their own defaults (4 / 6 / 8 CTAs per SM)
   if (variant_.minb > 0) fill16_minb_ = variant_.minb;     // SEQALK_FILL_MINB
   if (const char *e = std::getenv("SEQALK_FILL_CTAS_PER_SM")) fill16_cap_ = std::max(0, std::atoi(e));
@@ -863,6 +866,15 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     fa.rebase_shift = fill16_shift_;
     fa.main_rp = main_rp_;
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 0], st));
+    if (one_launch && (fill16_flags_ & FILL16_SENT)) {
+      // sentinel hand-off (fill16.cu): the kept rows that pass from one strip pair to the next start out as
+      // FILL16_SENTINEL words
+      uint64_t max_words = 0;
+      for (size_t p = 0; p < B.count; ++p)
+        if (hp[p].nstrips > 1) max_words = std::max<uint64_t>(max_words, (uint64_t)(hp[p].nstrips - 1) * 4 * (uint64_t)macro_cols(hp[p].n));
+      if (max_words)
+        SEQALK_CUDA(launch_fill16_sentinels(fa.pairs, (uint32_t)B.count, fa.brow, main_rp_, max_words, st));
+    }
     if (one_launch) {
       SEQALK_CUDA(launch_fill16(fa, 100 + main_rp_, fill16_minb_, sm_count_, st, fill16_flags_, fill16_cap_));
     } else if (fill16_shift_) {
@@ -1030,8 +1042,9 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const double threads = (double)std::min<uint64_t>(std::min<uint64_t>(hw, 16), 2 * B.count);
         // measured: the 200k x 200k pair 15.3 ms -> 0.6 ms, the 78 pairs of big13 (18.7 MB of strings) 10.2 -> 3.2 ms
-        const double device_ns = 55.0 * (double)longest, host_ns = 4.0 * (double)total / threads + 100e3;
-        bool host = few_pairs_ && B.count > 0 && host_ns < device_ns;
+        // (only where it pays clearly: small jobs stay on the GPU)
+        const double device_ns = 55.0 * (double)longest, host_ns = 2.5 * (double)total / threads + 200e3;
+        bool host = few_pairs_ && B.count > 0 && device_ns > 1.5e6 && 1.5 * host_ns < device_ns;
         if (const char *e = std::getenv("SEQALK_HOST_HASH")) host = std::atoi(e) != 0 && B.count > 0;
         if (host) {
           host_hash_batch(S, G, B.count, B.out_bytes, digests_dev, hs, st);

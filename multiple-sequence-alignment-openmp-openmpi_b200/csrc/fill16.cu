@@ -150,7 +150,11 @@ __device__ __forceinline__ unsigned row_table16(bool inside, unsigned ch, unsign
 // instead of a branch that one lane takes at every step (see below).
 // PIPE: the lane hand-off is shuffled as soon as a column is done (macro_step16_sh) and the staged
 // entries of the next step are read from shared memory one step ahead.
-template <int RP, bool PREDCK = false, bool PIPE = false>
+// SENT: no progress counters — the predecessor's bottom row itself says whether it is there: the engine
+// fills the hand-off rows with FILL16_SENTINEL words before the launch, a block of 32 macro columns is
+// staged once none of its words is the sentinel any more (one L2 round trip per attempt instead of
+// poll + acquire + load, and no release fence on the producer's side).  H' can never take that value.
+template <int RP, bool PREDCK = false, bool PIPE = false, bool SENT = false>
 __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const PairDesc &P, const int s,
                                                    const int row_base, const int lane, uint2 *ring_sel,
                                                    int4 *ring_top) {
@@ -268,7 +272,7 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
     // ---- stage the block's 32 stream entries: selector words of macro column e (low halves) /
     // e - 32 (high halves), and the predecessor's bottom row at macro column e (lane 0's top row)
     const int e = q0 + lane;
-    if (!first) {
+    if (!first && !SENT) {
       const int need = min(nq, q0 + 32);
       if (avail < need) {
         // relaxed polls (an acquire load invalidates the SM's L1), one acquire once the value is there
@@ -289,11 +293,19 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
     const uint2 sv = e < nq + 64 ? __ldg(selstream + e) : make_uint2(SEL_NULL, SEL_NULL);
     int4 tv = make_int4(0, 0, 0, 0);
     if (!first) {
-      if (e < nq) {
-        tv = __ldcg(brow_rd + e);
-      } else {  // past the last column: keep copying it (the halves keep running with cost 0)
-        const int lastv = __ldcg(reinterpret_cast<const int *>(brow_rd) + 4 * nq - 1);
-        tv = make_int4(lastv, lastv, lastv, lastv);
+      unsigned ns = 32;
+      for (;;) {
+        if (e < nq) {
+          tv = __ldcg(brow_rd + e);
+        } else {  // past the last column: keep copying it (the halves keep running with cost 0)
+          const int lastv = __ldcg(reinterpret_cast<const int *>(brow_rd) + 4 * nq - 1);
+          tv = make_int4(lastv, lastv, lastv, lastv);
+        }
+        if (!SENT) break;
+        const int S = (int)FILL16_SENTINEL;
+        if (__all_sync(FULL, tv.x != S && tv.y != S && tv.z != S && tv.w != S)) break;
+        __nanosleep(ns);
+        if (ns < 1024) ns *= 2;
       }
     }
     __syncwarp();
@@ -399,7 +411,7 @@ __device__ __forceinline__ void process_strip_pair(const FillArgs &a, const Pair
     }
     // ---- publish the progress of the bottom row (virtual lane 63 = lane 31's high halves), once
     // per block: the next strip pair consumes it in blocks of 32 columns as well
-    if (!last) {
+    if (!last && !SENT) {
       const int done = min(nq, q0 + send - 63);
       if (done > 0 && lane == 31) st_release_u32(my_progress, (unsigned)done);
     }
@@ -438,7 +450,7 @@ __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_kernel(const FillArg
 // predecessor through the same progress counters as every other strip pair.  One queue, one
 // ramp-down per batch instead of three (the tail launches of a small batch — one GPU's share of a
 // chunk on 8 GPUs — are shorter than one wave of warps).
-template <int MAINRP, int MINB, bool PREDCK = false, bool PIPE = false>
+template <int MAINRP, int MINB, bool PREDCK = false, bool PIPE = false, bool SENT = false>
 __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_all_kernel(const FillArgs a) {
   __shared__ uint2 s_sel[F16_THREADS / 32][128];
   __shared__ int4 s_top[F16_THREADS / 32][32];
@@ -453,11 +465,11 @@ __global__ void __launch_bounds__(F16_THREADS, MINB) fill16_all_kernel(const Fil
     const int s = (int)task.strip;
     const int nmain = main_strips(P.nstrips, P.half_last);
     if (s < nmain)
-      process_strip_pair<MAINRP, PREDCK && MAINRP >= 8, PIPE>(a, P, s, s * (64 * MAINRP), lane, s_sel[warp], s_top[warp]);
+      process_strip_pair<MAINRP, PREDCK && MAINRP >= 8, PIPE, SENT>(a, P, s, s * (64 * MAINRP), lane, s_sel[warp], s_top[warp]);
     else if (MAINRP == 32 && (P.half_last & 2) && s == nmain)
       process_strip_pair<16, PREDCK>(a, P, s, nmain * 2048, lane, s_sel[warp], s_top[warp]);
     else
-      process_strip_pair<8, PREDCK>(a, P, s, (int)P.mpad - 512, lane, s_sel[warp], s_top[warp]);
+      process_strip_pair<8, PREDCK, false, SENT>(a, P, s, (int)P.mpad - 512, lane, s_sel[warp], s_top[warp]);
   }
 }
 
@@ -484,6 +496,20 @@ __global__ void build_sel16_kernel(const uint8_t *__restrict__ codes, uint8_t *_
   }
 }
 
+// FILL16_SENT: fills the hand-off rows of every pair (the kept row above each strip pair but the first)
+// with sentinel words.  blockIdx.y = pair.
+__global__ void fill16_sentinel_kernel(const PairDesc *__restrict__ pairs, int32_t *__restrict__ brow, int rows_per_pair) {
+  const PairDesc P = pairs[blockIdx.y];
+  const int nq = (P.n + 3) >> 2;
+  const uint64_t bstride = (uint64_t)(4 * nq + 4);
+  const int4 sent = make_int4((int)FILL16_SENTINEL, (int)FILL16_SENTINEL, (int)FILL16_SENTINEL, (int)FILL16_SENTINEL);
+  const long long total = (long long)(P.nstrips - 1) * nq;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(t / nq) + 1, q = (int)(t - (long long)(s - 1) * nq);
+    reinterpret_cast<int4 *>(brow + P.brow_off + ((uint64_t)s * rows_per_pair - 1) * bstride)[q] = sent;
+  }
+}
+
 typedef void (*Fill16Ptr)(const FillArgs);
 // the one-launch kernel; flags: FILL16_PREDCK / FILL16_PIPE
 Fill16Ptr pick16_all(int rp, int minb, int flags) {
@@ -495,11 +521,13 @@ Fill16Ptr pick16_all(int rp, int minb, int flags) {
     return minb == 3 ? fill16_all_kernel<32, 3> : fill16_all_kernel<32, 4>;
   }
   if (rp == 16) {
+    if (predck && (flags & FILL16_SENT)) return fill16_all_kernel<16, 3, true, false, true>;
     if (predck) return minb == 6 ? fill16_all_kernel<16, 6, true> : fill16_all_kernel<16, 3, true>;
     return minb == 5 ? fill16_all_kernel<16, 5> : fill16_all_kernel<16, 6>;
   }
   // thin strip pairs (512 / 256 rows) for jobs of a few long pairs: more warps along the wavefront
   if (rp == 8) {
+    if (predck && pipe && (flags & FILL16_SENT)) return fill16_all_kernel<8, 4, true, true, true>;  // uniform strip pairs only
     if (predck && pipe) return minb == 8 ? fill16_all_kernel<8, 8, true, true> : fill16_all_kernel<8, 4, true, true>;
     return predck ? fill16_all_kernel<8, 8, true> : fill16_all_kernel<8, 8>;
   }
@@ -541,6 +569,14 @@ cudaError_t launch_build_sel16(const uint8_t *codes, uint8_t *sel16, const uint3
   const int entries = ((maxlen + 3) >> 2) + 64;
   dim3 grid((unsigned)std::min(64, (entries + 255) / 256), (unsigned)k);
   build_sel16_kernel<<<grid, 256, 0, stream>>>(codes, sel16, off_dev, len_dev, k);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill16_sentinels(const PairDesc *pairs, uint32_t npairs, int32_t *brow, int main_rp, uint64_t max_words,
+                                    cudaStream_t stream) {
+  if (npairs == 0) return cudaSuccess;
+  const unsigned bx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(64, (max_words / 4 + 255) / 256));
+  fill16_sentinel_kernel<<<dim3(bx, npairs), 256, 0, stream>>>(pairs, brow, 64 * main_rp / TILE_ROWS);
   return cudaGetLastError();
 }
 

@@ -171,10 +171,16 @@ cudaError_t launch_fill(const FillArgs &args, const FillVariant &v, int sm_count
 // flags (one-launch kernel, rp >= 100): FILL16_PREDCK = column checkpoints by predicated stores through a running
 // pointer instead of a one-lane branch; FILL16_PIPE = lane hand-off shuffled as soon as a column is done, staged
 // entries read one step ahead (8 rows per half lane).  max_ctas_per_sm > 0 caps the resident CTAs.
-enum : int { FILL16_PREDCK = 1, FILL16_PIPE = 2 };
+// FILL16_SENT (with FILL16_PREDCK; 8 or 16 rows per half lane, where a pair's strip pairs start every 64 * rp
+// rows): hand-off rows pre-filled with FILL16_SENTINEL by the engine replace the progress counters.
+enum : int { FILL16_PREDCK = 1, FILL16_PIPE = 2, FILL16_SENT = 4 };
+constexpr uint32_t FILL16_SENTINEL = 0x80808080u;  // a byte pattern (cudaMemset2DAsync) no H' can take: |H'| < 2^29
 cudaError_t launch_fill16(const FillArgs &args, int rp, int minb, int sm_count, cudaStream_t stream, int flags = 0,
                           int max_ctas_per_sm = 0);
 int fill16_blocks_per_sm(int rp, int minb, int flags = 0);
+// FILL16_SENT: sentinel words into every pair's hand-off rows (max_words: the most any pair needs, sizes the grid)
+cudaError_t launch_fill16_sentinels(const PairDesc *pairs, uint32_t npairs, int32_t *brow, int main_rp, uint64_t max_words,
+                                    cudaStream_t stream);
 int fill16_rebase_shift(int pxy, int pgap, int rp);  // 0: penalties do not fit the 16-bit scheme with rp rows per half lane
 cudaError_t launch_build_sel16(const uint8_t *codes, uint8_t *sel16, const uint32_t *off_dev, const int32_t *len_dev,
                                int k, int maxlen, cudaStream_t stream);

@@ -342,6 +342,8 @@ def test_cfg5_full_size_properties(seqalk, oracle, workloads):
     {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "16", "SEQALK_FILL_MINB": "6"},
     {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "16", "SEQALK_FILL16_PREDCK": "0", "SEQALK_FILL_CTAS_PER_SM": "1"},
     {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_FILL16_PIPE": "0"},
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_SENT": "0"},  # progress counters instead of sentinel hand-off rows
+    {"SEQALK_FILL_R": "32", "SEQALK_FILL16_SENT": "1", "SEQALK_DIR_BUDGET_GB": "0.001", "SEQALK_SLOTS": "2"},
     {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_FILL16_PIPE": "1", "SEQALK_FILL_MINB": "8"},
     {"SEQALK_FILL_R": "32", "SEQALK_FILL16_RP": "8", "SEQALK_FILL16_PREDCK": "0", "SEQALK_FILL16_PIPE": "0",
      "SEQALK_DIR_BUDGET_GB": "0.001"},
