@@ -872,8 +872,10 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       uint64_t max_words = 0;
       for (size_t p = 0; p < B.count; ++p)
         if (hp[p].nstrips > 1) max_words = std::max<uint64_t>(max_words, (uint64_t)(hp[p].nstrips - 1) * 4 * (uint64_t)macro_cols(hp[p].n));
-      if (max_words)
+      if (max_words) {
         SEQALK_CUDA(launch_fill16_sentinels(fa.pairs, (uint32_t)B.count, fa.brow, main_rp_, max_words, st));
+        stats_.fill_launches++;
+      }
     }
     if (one_launch) {
       SEQALK_CUDA(launch_fill16(fa, 100 + main_rp_, fill16_minb_, sm_count_, st, fill16_flags_, fill16_cap_));
