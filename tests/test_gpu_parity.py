@@ -170,7 +170,8 @@ def test_batching_does_not_change_results(seqalk, oracle, workloads, monkeypatch
         job.run()
         pen, dig = job.fetch()
         st = job.stats()
-    assert st.batches > 5 and st.fill_launches == st.batches
+    # one persistent fill launch per batch (+ the sentinel rows of a few-pair job's batches, fill16.cu)
+    assert st.batches > 5 and st.batches <= st.fill_launches <= 2 * st.batches
     assert st.cells == workloads.total_cells(genes)
     assert seqalk.fold_chain(dig) == d1 and np.array_equal(pen, p1)
     od, op, _ = oracle.all_pairs(genes, 3, 2)
