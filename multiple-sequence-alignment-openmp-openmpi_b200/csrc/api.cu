@@ -529,8 +529,11 @@ int seqalk_all_pairs(const char *const *seqs, const int32_t *lens, int32_t k, in
       for (double &v : r.prof) v = 0;
       DeviceWorker &w = *r.workers[0];
       w.load(pack);
+      const double t_load = ms_since();
       w.plan(tasks, pxy, pgap);
       r.prof[1] = ms_since();
+      if (const char *e = std::getenv("SEQALK_TRACE"))
+        if (std::atoi(e) >= 2) std::fprintf(stderr, "[seqalk call] load %.3f ms, plan %.3f ms (after packing)\n", t_load, r.prof[1] - t_load);
       w.run_and_fold(penalties_out, digest_hex_out);
       const JobStats &st = w.stats();
       r.prof[0] = ms_since();

@@ -414,8 +414,17 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
      // traceback of batch b).  Tile mode: one set per pipeline — 3 x 40 GB by default
      // (SEQALK_SLOTS / SEQALK_DIR_BUDGET_GB), 104 GB without overlap.
     SEQALK_CUDA(cudaSetDevice(dev_));
-    size_t free_b = 0, total_b = 0;
-    SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // our own (cached) buffers count as available, so "free + own" does not change from job to job:
+    // asked once per worker — cudaMemGetInfo costs 0.5 - 15 ms with tens of GB allocated, which showed
+    // in the end-to-end time of the 40 ms big13 job (SEQALK_TRACE=2)
+    auto ask = [&]() {
+      size_t free_b = 0, total_b = 0;
+      SEQALK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      size_t own = 0;
+      for (const Slot &s : slots_) own += s.dirs.cap + s.brow.cap;
+      mem_avail_ = free_b + own;
+    };
+    if (!mem_avail_) ask();
     // tile mode: consecutive batches go to different pipelines (own set of the big arrays, own
     // streams), so the tail of one batch's fill / traceback / digest is filled by the next
     // batches' kernels (SEQALK_OVERLAP=0: one set, stages back to back).  One GPU's share of an
@@ -428,10 +437,11 @@ void DeviceWorker::plan(const std::vector<TaskIJ> &tasks, int pxy, int pgap,
     double budget_gb = tiles_ ? (nbig >= 3 ? 40.0 : 104.0 / nbig) : 56.0;
     if (const char *e = std::getenv("SEQALK_DIR_BUDGET_GB")) budget_gb = std::atof(e);
     dir_budget_ = (size_t)(budget_gb * (double)(1ull << 30));
-    // our own (cached) buffers count as available
-    size_t own = 0;
-    for (const Slot &s : slots_) own += s.dirs.cap + s.brow.cap;
-    const size_t cap = (size_t)((double)(free_b + own) * 0.80 / nbig);
+    size_t cap = (size_t)((double)mem_avail_ * 0.80 / nbig);
+    if (dir_budget_ > cap) {  // memory is tight (a shared device, other workers' caches): look again
+      ask();
+      cap = (size_t)((double)mem_avail_ * 0.80 / nbig);
+    }
     if (dir_budget_ > cap) dir_budget_ = cap;
   }
   mixed_ = tiles_;  // 512-row last strips where they halve the row padding
@@ -623,6 +633,16 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
   SEQALK_CUDA(cudaSetDevice(dev_));
   const bool streaming = fold_hex != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
+  // SEQALK_TRACE=2: host-side time stamps of this run on stderr (ms since its start)
+  const bool trace = [] {
+    const char *e = std::getenv("SEQALK_TRACE");
+    return e && std::atoi(e) >= 2;
+  }();
+  std::vector<std::pair<const char *, double>> marks;
+  auto mark = [&](const char *what) {
+    if (trace)
+      marks.push_back({what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count()});
+  };
   const int R = variant_.R;
   const size_t T = tasks_.size();
   results_in_caller_pen_ = penalties_dev != nullptr;
@@ -718,6 +738,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       ensure(G.cost, need_.count * sizeof(int32_t));
       ensure(S.counter, 4 * sizeof(uint32_t));
     } while (dropped_cached_);
+    mark("buffers sized");
     // ---- build descriptors in pinned staging
     const size_t pairs_bytes = round_up(need_.count * sizeof(PairDesc), 256);
     const size_t tasks_bytes = round_up((size_t)need_.nstrips * sizeof(StripTask), 256);
@@ -834,6 +855,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
         if (hp[p].half_last & 1) ht[n_main + n_mid + n_half++] = StripTask{(uint32_t)p, (uint32_t)(hp[p].nstrips - 1)};
     }
     S.last_pairs.assign(hp, hp + B.count);
+    mark("descriptors built");
     // ---- enqueue: fill stream
     cudaStream_t st = tiles_ ? tile_stream : fill_stream_;
     if (S.post_pending) {  // the slot's buffers are free once its previous batch is post-processed
@@ -909,6 +931,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     }
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 1], st));
     SEQALK_CUDA(cudaEventRecord(S.fill_done, st));
+    mark("fill enqueued");
     // ---- enqueue: post stream (high priority; runs under the next batch's fill).  In tile
     // mode the traceback is a heavy kernel of its own: the stages run back to back instead.
     // Tile mode, overlapped pipelines: traceback + digest of a batch go to the pipeline's own
@@ -997,6 +1020,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     }
     if (!fill_only) SEQALK_CUDA(tiles_ ? launch_traceback_tiles(ta, st) : launch_traceback(ta, st));
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 3], st));
+    mark("traceback enqueued");
 
     if (scores_only) {
       ScoreArgs sa;
@@ -1056,6 +1080,7 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
       SEQALK_CUDA(launch_digest(da, st));
     }
     SEQALK_CUDA(cudaEventRecord(ev_[EV * b + 4], st));
+    mark("digest enqueued (after the host hashes, if any)");
     if (streaming) {
       SEQALK_CUDA(cudaMemcpyAsync(h_pen + B.first, penalties_dev + B.first, B.count * sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, st));
@@ -1084,15 +1109,20 @@ void DeviceWorker::run_impl(int32_t *penalties_dev, uint8_t *digests_dev, int32_
     if (!fill_only) stats_.traceback_launches++;
     stats_.digest_launches++;
   }
+  mark("all batches enqueued");
   if (streaming) fold_ready(true, batch_end);
+  mark("results folded");
   SEQALK_CUDA(cudaStreamSynchronize(fill_stream_));
   SEQALK_CUDA(cudaStreamSynchronize(post_stream_));
   SEQALK_CUDA(cudaStreamSynchronize(fill2_stream_));
   for (cudaStream_t st : more_streams_) SEQALK_CUDA(cudaStreamSynchronize(st));
   for (cudaStream_t st : pipe_post_streams_) SEQALK_CUDA(cudaStreamSynchronize(st));
   for (Slot &S : slots_) S.staged_pending = S.post_pending = false;
+  mark("streams idle");
   if (batch_end == batches_.size() && !scores_only) verify_check();
   ran_ = true;
+  mark("self-check read");
+  for (const auto &m : marks) std::fprintf(stderr, "[seqalk run] %8.3f ms  %s\n", m.second, m.first);
   for (size_t b = batch_begin; b < batch_end; ++b) {
     float ms = 0;
     SEQALK_CUDA(cudaEventElapsedTime(&ms, ev_[EV * b + 0], ev_[EV * b + 1]));

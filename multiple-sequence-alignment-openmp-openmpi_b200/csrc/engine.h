@@ -145,6 +145,7 @@ class DeviceWorker {
   int dev_;
   int sm_count_ = 0;
   size_t dir_budget_ = 0;
+  size_t mem_avail_ = 0;  // free device memory + our own cached big arrays, asked once (plan)
   int nslots_ = 2;
   std::vector<Slot> slots_;
   cudaStream_t fill_stream_ = nullptr, post_stream_ = nullptr;

@@ -41,8 +41,12 @@
 //     since the two halves reach a checkpoint column 32 steps apart; CKQ = 32: both halves are at a
 //     checkpoint column at the same step, image e = [rows of A at checkpoint e | rows of B at
 //     checkpoint e - 1].  The traceback unpacks with the logged base.
+//
+// Builds of the one-launch kernel (FILL16_* flags, chosen per job shape by engine.cu):
+// column checkpoints by predicated stores (PREDCK) instead of a one-lane branch; for jobs of a few long
+// pairs the lane hand-off shuffled as soon as a column is done (PIPE) and sentinel words in the
+// hand-off rows instead of progress counters (SENT).
 #include <algorithm>
-#include <cstdlib>
 
 #include "fill_core.cuh"
 

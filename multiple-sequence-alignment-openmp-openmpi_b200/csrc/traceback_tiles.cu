@@ -7,10 +7,13 @@
 // the recompute runs the very same per-cell update as the fill (fill_core.cuh, EMIT = true), so
 // the 2-bit codes — and with them the tie-breaking — are identical to the directions mode.
 //
-// Half a warp per pair (jobs with many pairs; a whole warp + three look-ahead warps for jobs of a
-// few long pairs).  Per tile: lane t owns RT rows, the lanes sweep the needed macro columns as a
-// skewed wavefront (exactly like the fill) writing the codes to shared memory, then walk the path
-// inside the tile until it leaves through the top or the left edge.
+// Half a warp per pair (jobs with many pairs).  Per tile: lane t owns RT rows, the lanes sweep the
+// needed macro columns as a skewed wavefront (exactly like the fill) writing the codes to shared
+// memory, then walk the path inside the tile until it leaves through the top or the left edge.
+// Jobs of a few LONG pairs run the banded traceback in chapters instead (further down): all tiles
+// near the path recomputed at once together with their transfer tables, one table look-up per tile
+// to follow the path, all visited tiles walked at once; shorter few-pair jobs keep the four-warp kernel
+// (walk + three look-ahead recompute warps).
 #include "fill_core.cuh"
 
 namespace seqalk {
