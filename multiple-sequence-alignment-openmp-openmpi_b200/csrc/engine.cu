@@ -314,6 +314,7 @@ void DeviceWorker::ensure(DevBuf &b, size_t bytes) {
     e = cudaMalloc(&b.p, want);
   }
   if (e != cudaSuccess) {
+    mem_avail_ = 0;  // the next plan() looks at the free memory again
     char msg[256];
     std::snprintf(msg, sizeof msg, "getMinimumPenalty: device allocation of %zu bytes failed (%s)", want,
                   cudaGetErrorString(e));
