@@ -167,3 +167,22 @@ def test_chunk_bounds_shrink_geometrically(seqalk):
         assert np.allclose(sizes[1:] / sizes[:-1], 0.8, atol=0.01)
     assert sum(np.diff(seqalk.chunk_bounds(T, 14))[-3:]) < 0.05 * T
     assert seqalk.chunk_bounds(100, 4) == [0, 25, 50, 75, 100]
+
+
+def test_every_knob_in_the_sources_is_documented():
+    """INTEGRATION.md section 4 lists every SEQALK_* environment knob the library or the package reads."""
+    import glob
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg_dir = os.path.join(root, "multiple-sequence-alignment-openmp-openmpi_b200")
+    knobs = set()
+    for path in glob.glob(os.path.join(pkg_dir, "csrc", "*")) + glob.glob(os.path.join(pkg_dir, "*.py")):
+        if os.path.isfile(path) and path.endswith((".cu", ".cpp", ".h", ".cuh", ".py")):
+            text = open(path, errors="replace").read()
+            knobs.update(re.findall(r'getenv\("(SEQALK_[A-Z0-9_]+)"\)', text))
+            knobs.update(re.findall(r'environ(?:\.get\(|\[)"(SEQALK_[A-Z0-9_]+)"', text))
+    assert len(knobs) > 20
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(k for k in knobs if k not in doc)
+    assert not missing, missing
